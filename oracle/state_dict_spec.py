@@ -1,0 +1,139 @@
+"""The reference's `VIMAPolicy.state_dict()` contract: key -> shape (TEST INFRASTRUCTURE).
+
+Written out by hand from the reference constructors (vima/policy/vima_policy.py:12-114 and the vima.nn
+modules it wires up) so that tests on the GPU box -- where /root/reference does not exist -- can build
+shared weights and check the product's `load_state_dict(strict=True)` compatibility.
+`tests/test_state_dict_contract.py::test_spec_matches_reference` compares it with the real thing in the
+build container.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+ACTION_DIMS = OrderedDict(
+    pose0_position=[50, 100], pose0_rotation=[50] * 4, pose1_position=[50, 100], pose1_rotation=[50] * 4
+)
+ACTION_IN = OrderedDict(pose0_position=2, pose0_rotation=4, pose1_position=2, pose1_rotation=4)
+
+
+def xattn_gpt_spec(prefix: str, E: int, n_layer: int, n_positions: int = 512, xattn_n_positions: int = 256, geglu=True):
+    sd = OrderedDict()
+    sd[prefix + "position_ids"] = (n_positions,)
+    sd[prefix + "xattn_position_ids"] = (xattn_n_positions,)
+    sd[prefix + "positions_embed.weight"] = (n_positions, E)
+    sd[prefix + "xattn_positions_embed.weight"] = (xattn_n_positions, E)
+    for i in range(n_layer):
+        h = f"{prefix}h.{i}."
+        sd[h + "attn.bias"] = (1, 1, n_positions, n_positions)
+        sd[h + "attn.c_attn.weight"] = (E, 3 * E)
+        sd[h + "attn.c_attn.bias"] = (3 * E,)
+        sd[h + "attn.c_proj.weight"] = (E, E)
+        sd[h + "attn.c_proj.bias"] = (E,)
+        sd[h + "ln_1.weight"] = (E,)
+        sd[h + "ln_1.bias"] = (E,)
+        sd[h + "mlp.c_fc.weight"] = (E, 4 * E)
+        sd[h + "mlp.c_fc.bias"] = (4 * E,)
+        sd[h + "mlp.c_proj.weight"] = (4 * E, E)
+        sd[h + "mlp.c_proj.bias"] = (E,)
+        if geglu:
+            sd[h + "mlp.gated_layer.weight"] = (4 * E, E)
+        sd[h + "ln_2.weight"] = (E,)
+        sd[h + "ln_2.bias"] = (E,)
+    for i in range(n_layer):
+        x = f"{prefix}xattns.{i}."
+        sd[x + "kv_position_ids"] = (xattn_n_positions,)
+        sd[x + "layernorm.weight"] = (E,)
+        sd[x + "layernorm.bias"] = (E,)
+        sd[x + "query.weight"] = (E, E)
+        sd[x + "key_value.weight"] = (2 * E, E)
+        sd[x + "attention_out.weight"] = (E, E)
+        sd[x + "ln.weight"] = (E,)
+        sd[x + "ln.bias"] = (E,)
+        sd[x + "linear1.weight"] = (4 * E, E)
+        sd[x + "linear2.weight"] = (E, 4 * E)
+        if geglu:
+            sd[x + "gated_layer.weight"] = (4 * E, E)
+    return sd
+
+
+def vit_spec(prefix: str, width=768, layers=4, res=32, patch=16, out=768):
+    sd = OrderedDict()
+    sd[prefix + "cls_token"] = (width,)
+    sd[prefix + "pos_embed"] = ((res // patch) ** 2 + 1, width)
+    sd[prefix + "projection"] = (width, out)
+    sd[prefix + "conv1.weight"] = (width, 3, patch, patch)
+    sd[prefix + "ln_pre.weight"] = (width,)
+    sd[prefix + "ln_pre.bias"] = (width,)
+    for i in range(layers):
+        b = f"{prefix}blocks.{i}."
+        sd[b + "attn.in_proj_weight"] = (3 * width, width)
+        sd[b + "attn.in_proj_bias"] = (3 * width,)
+        sd[b + "attn.out_proj.weight"] = (width, width)
+        sd[b + "attn.out_proj.bias"] = (width,)
+        sd[b + "ln_1.weight"] = (width,)
+        sd[b + "ln_1.bias"] = (width,)
+        sd[b + "mlp.c_fc.weight"] = (4 * width, width)
+        sd[b + "mlp.c_fc.bias"] = (4 * width,)
+        sd[b + "mlp.c_proj.weight"] = (width, 4 * width)
+        sd[b + "mlp.c_proj.bias"] = (width,)
+        sd[b + "ln_2.weight"] = (width,)
+        sd[b + "ln_2.bias"] = (width,)
+    sd[prefix + "ln_post.weight"] = (width,)
+    sd[prefix + "ln_post.bias"] = (width,)
+    return sd
+
+
+def mlp_spec(prefix: str, dims):
+    """build_mlp Sequential: Linear at 0,3,6,... (Identity norm + ReLU in between)."""
+    sd = OrderedDict()
+    for j in range(len(dims) - 1):
+        sd[f"{prefix}{3 * j}.weight"] = (dims[j + 1], dims[j])
+        sd[f"{prefix}{3 * j}.bias"] = (dims[j + 1],)
+    return sd
+
+
+def t5_spec(prefix: str, d_model=768, d_ff=3072, n_layers=12, n_heads=12, d_kv=64, vocab=32128, buckets=32):
+    sd = OrderedDict()
+    sd[prefix + "shared.weight"] = (vocab, d_model)
+    sd[prefix + "encoder.embed_tokens.weight"] = (vocab, d_model)
+    for i in range(n_layers):
+        b = f"{prefix}encoder.block.{i}."
+        for n in "qkv":
+            sd[b + f"layer.0.SelfAttention.{n}.weight"] = (n_heads * d_kv, d_model)
+        sd[b + "layer.0.SelfAttention.o.weight"] = (d_model, n_heads * d_kv)
+        if i == 0:
+            sd[b + "layer.0.SelfAttention.relative_attention_bias.weight"] = (buckets, n_heads)
+        sd[b + "layer.0.layer_norm.weight"] = (d_model,)
+        sd[b + "layer.1.DenseReluDense.wi.weight"] = (d_ff, d_model)
+        sd[b + "layer.1.DenseReluDense.wo.weight"] = (d_model, d_ff)
+        sd[b + "layer.1.layer_norm.weight"] = (d_model,)
+    sd[prefix + "encoder.final_layer_norm.weight"] = (d_model,)
+    return sd
+
+
+def state_dict_spec(*, embed_dim: int, xf_n_layers: int, sattn_n_heads: int = 0, xattn_n_heads: int = 0):
+    E = embed_dim
+    sd = OrderedDict()
+    sd.update(xattn_gpt_spec("xattn_gpt.", E, xf_n_layers))
+    sd.update(vit_spec("obj_encoder.cropped_img_encoder.vit."))
+    for v in ("front", "top"):
+        sd.update(mlp_spec(f"obj_encoder.bbox_mlp.{v}.", [4, 768, 768, 768]))
+    for v in ("front", "top"):
+        sd[f"obj_encoder.pre_transformer_layer.{v}.weight"] = (E, 1536)
+        sd[f"obj_encoder.pre_transformer_layer.{v}.bias"] = (E,)
+    sd["end_effector_encoder.weight"] = (2, 2)
+    sd["obs_fusion_layer.weight"] = (E, E + 2)
+    sd["obs_fusion_layer.bias"] = (E,)
+    for k, n_in in ACTION_IN.items():
+        sd.update(mlp_spec(f"action_encoder._embed_dict.{k}._layer.", [n_in, 256, 256]))
+    sd["action_encoder._post_layer.weight"] = (E, 1024)
+    sd["action_encoder._post_layer.bias"] = (E,)
+    for k, dims in ACTION_DIMS.items():
+        for j, n in enumerate(dims):
+            sd.update(mlp_spec(f"action_decoder._decoders.{k}.mlps.{j}.", [E, 512, 512, n]))
+    sd["prompt_embedding._embed_layer.weight"] = (32128, 768)
+    sd.update(t5_spec("t5_prompt_encoder.t5."))
+    if E != 768:
+        sd["t5_prompt_encoder_post_layer.weight"] = (E, 768)
+    sd.update(mlp_spec("prompt_obj_post_layer.", [E, 768, 768, 768]))
+    return sd
