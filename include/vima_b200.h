@@ -1,0 +1,183 @@
+/*
+ * vima_b200 -- C ABI of the B200 (sm_100a) kernels behind the VIMA policy forward pass.
+ *
+ * The reference (vimalabs/VIMA) is pure Python/PyTorch and has no FFI of its own; its
+ * operator surface is the `vima.nn` module tree.  Every entry point below replaces the arithmetic of one
+ * reference module `forward` (cited per function, paths relative to the reference root; `HF:` = the
+ * `transformers` package it subclasses) and is what a maintainer would bind from those modules -- see
+ * INTEGRATION.md for the ctypes stub.
+ *
+ * Conventions
+ *   - plain C: raw DEVICE pointers, explicit sizes / leading dimensions (in elements), a `cudaStream_t` passed
+ *     as `void*`.  No torch types.  The caller owns every buffer; the library owns only the context.
+ *   - every call is asynchronous on the given stream and performs no host synchronisation.
+ *   - return value: 0 = ok, otherwise a VIMA_E_* code; `vima_last_error(ctx)` gives the message.  Never throws.
+ *   - one context per (device, host thread); not thread-safe.
+ *   - 16-bit GEMM operands: activations and packed weights are K-major arrays of fp16 (VIMA_DT_F16) or bf16
+ *     (VIMA_DT_BF16).  In split mode every operand is a (hi, lo) PAIR of such arrays with x ~= hi + lo and the
+ *     kernels accumulate hi*hi + lo*hi + hi*lo in fp32, which reproduces the reference's fp32 products to
+ *     ~1e-5 rel end to end (DESIGN.md "operand precision").  `lo == NULL` selects single-pass mode.
+ *   - `ld*` of 16-bit operand arrays must be multiples of 8 elements and base pointers 16-byte aligned (TMA).
+ */
+#ifndef VIMA_B200_H
+#define VIMA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#pragma GCC visibility push(default)
+
+#define VIMA_B200_ABI_VERSION 1
+
+enum { VIMA_OK = 0, VIMA_E_INVALID = 1, VIMA_E_CUDA = 2, VIMA_E_UNSUPPORTED = 3 };
+enum { VIMA_DT_F16 = 0, VIMA_DT_BF16 = 1 };
+enum { VIMA_ACT_NONE = 0, VIMA_ACT_RELU = 1, VIMA_ACT_QUICKGELU = 2, VIMA_ACT_GELU = 3 };
+
+typedef struct vima_ctx vima_ctx;
+
+int vima_abi_version(void);
+/* Creates a context on `device` (cudaSetDevice is applied inside every call). Fails if the device is not sm_100. */
+int vima_create(vima_ctx** out, int device);
+void vima_destroy(vima_ctx* ctx);
+const char* vima_last_error(vima_ctx* ctx);
+int vima_sm_count(vima_ctx* ctx);
+/* Number of kernels this context has launched so far (bench.py's `gpu_launches`). */
+int64_t vima_launch_count(vima_ctx* ctx);
+
+/* ---- operand preparation ------------------------------------------------------------------------------- */
+/* fp32 [rows, cols] (ldx) -> 16-bit operands (hi, lo|NULL) [rows, ld16]; columns [cols, pad_cols) are zeroed. */
+int vima_split_f32(vima_ctx*, const float* x, int64_t rows, int cols, int ldx, void* hi, void* lo, int ld16, int pad_cols,
+                   float scale, int dtype, void* stream);
+/* Weight packing: w is [n, k] (nn.Linear.weight) or, if transposed != 0, [k, n] (HF Conv1D.weight,
+ * HF:pytorch_utils.py:97-123).  Output: K-major (hi, lo|NULL) [n, ld16], zero padded, multiplied by `scale`. */
+int vima_pack_weight(vima_ctx*, const float* w, int n, int k, int transposed, int ldw, void* hi, void* lo, int ld16, float scale,
+                     int dtype, void* stream);
+
+/* ---- tcgen05 GEMM: out = epilogue(A[M,K] * B[N,K]^T) ------------------------------------------------------
+ * Replaces every large Linear / Conv1D on the path: components.py:87-88,130-142 (c_attn, c_proj, c_fc, query,
+ * key_value, attention_out, linear1/2, gated_layer), vit.py:151-157,203-213 (conv1, in/out_proj, mlp),
+ * obj_encoder.py:86-93, prompt_encoder.py T5 q/k/v/o/wi/wo, vima_policy.py:49,97-108.
+ * Epilogue order: v = acc*acc_scale + bias[col]; v = act(v); GLU: v *= (acc2*acc_scale + bias[col2]);
+ * v *= mul[row,col]; v += residual[row,col]; store fp32 and/or (hi, lo).
+ * GLU mode: B holds, per tile of block_n accumulator columns, block_n/2 "value" rows followed by the matching
+ * block_n/2 "gate" rows (see vima_glu_block_n); N = 2 * output columns. */
+typedef struct {
+  int M, N, K;
+  const void *a_hi, *a_lo; /* [M, lda] */
+  int lda;
+  const void *b_hi, *b_lo; /* [N, ldb] packed weights */
+  int ldb;
+  int dtype;
+  int glu;
+  int act;
+  float acc_scale;
+  const float* bias;     /* [N] or NULL */
+  const float* mul;      /* fp32 [M, ld_mul] or NULL */
+  int ld_mul;
+  const float* residual; /* fp32 [M, ld_res] or NULL */
+  int ld_res;
+  float* out_f32;        /* or NULL */
+  int ld_o32;
+  void *out_hi, *out_lo; /* 16-bit outputs or NULL */
+  int ld_o16;
+  int block_n;           /* 0 = choose */
+} vima_gemm_desc;
+int vima_gemm(vima_ctx*, const vima_gemm_desc* d, void* stream);
+/* Accumulator tile width the GLU weight interleave must use for an output width of n_out columns. */
+int vima_glu_block_n(int n_out);
+
+/* ---- exact fp32 grouped GEMM (CUDA cores) for the tiny layers -------------------------------------------------
+ * action_decoder.py:151-166 (12 MLPs E->512->512->{50|100}), action_embd.py:29-56, obj_encoder.py:86 first layer.
+ * `groups` is a DEVICE array of n_groups descriptors; y[M, n] = act(x[M, k] * w[n, k]^T + b). */
+typedef struct {
+  const float* x; int ldx;
+  const float* w; int ldw;
+  const float* b;
+  float* y; int ldy;
+  int n, k;
+} vima_f32_gemm_group;
+int vima_gemm_f32_grouped(vima_ctx*, const vima_f32_gemm_group* groups_dev, int n_groups, int M, int max_n, int act, void* stream);
+
+/* ---- LayerNorm / T5 RMSNorm over rows ---------------------------------------------------------------------
+ * nn.LayerNorm eps 1e-5 (components.py:19,21,128,135; vit.py:164,168,204,214) and HF T5LayerNorm
+ * (HF:modeling_t5.py:46-68).  y1 = norm1(x + add); optional y2 = LayerNorm2(y1).  Outputs: y1 fp32, y2 fp32,
+ * and the LAST computed norm as (hi, lo) operands.  w == NULL skips norm1 (pure add / convert). cols % 4 == 0,
+ * cols <= 1024. */
+typedef struct {
+  const float* x; int64_t rows; int cols; int ldx;
+  const float* add; int ld_add;
+  const float* w; const float* b; float eps; int rms;
+  const float* w2; const float* b2; float eps2;
+  float* out_f32; int ld_o32;
+  float* out2_f32; int ld_o2;
+  void *out_hi, *out_lo; int ld_o16;
+  int dtype;
+} vima_norm_desc;
+int vima_norm(vima_ctx*, const vima_norm_desc* d, void* stream);
+
+/* ---- fused masked attention -----------------------------------------------------------------------------------
+ * Self-attention of the causal block (components.py:51-80: /sqrt(d), soft causal mask w*b + -1e4*(1-b), additive
+ * key mask finfo.min), cross-attention (components.py:179-214) and T5 self-attention (prompt_encoder.py:769-816:
+ * no scaling, shared relative-position bias + mask).  q/k/v/o pointers address head 0's first column; head h is
+ * at +h*D.  key_mask: uint8 [B, Lk] (1 = attend) or NULL.  rel_bias: fp32 [H, 2*Lk-1] indexed by (j-i+Lk-1). */
+typedef struct {
+  const void *q_hi, *q_lo; int ldq;
+  const void *k_hi, *k_lo; int ldk;
+  const void *v_hi, *v_lo; int ldv;
+  const uint8_t* key_mask;
+  const float* rel_bias;
+  void *o_hi, *o_lo; int ldo;
+  int B, H, Lq, Lk, D;
+  float scale;
+  int causal;
+  int dtype;
+} vima_attn_desc;
+int vima_attention(vima_ctx*, const vima_attn_desc* d, void* stream);
+
+/* nn.MultiheadAttention core on tiny sequences (ViT, vit.py:203,224-230): fp32 qkv [N*S, ld] (q|k|v, W wide each,
+ * bias included) -> (hi, lo) [N*S, ldo].  head_dim must be 32, S <= 16. */
+int vima_small_attention(vima_ctx*, const float* qkv, int ld, int64_t N, int S, int H, int W, float scale, void* o_hi, void* o_lo,
+                         int ldo, float* o_f32, int dtype, void* stream);
+
+/* ---- token assembly ------------------------------------------------------------------------------------------
+ * vima_policy.py:124-147: interleave obs (T,B,Q,E) / action (La,B,E) tokens into (L,B,E), L = T*Q + La; masks
+ * (B,L) uint8 (action slots 1); position ids (B,L) int64 = cumsum(mask)-1. */
+int vima_assemble_history(vima_ctx*, const float* obs, const uint8_t* obs_mask, const float* action, int T, int B, int Q, int E, int La,
+                          float* tokens, uint8_t* masks_bl, int64_t* pos_bl, void* stream);
+/* pos[b, l] = cumsum(mask[b, :l+1]) - 1   (vima_policy.py:147) */
+int vima_mask_cumsum(vima_ctx*, const uint8_t* mask, int B, int L, int64_t* pos, void* stream);
+/* out[b,l,:] = tok[b*stride_b + l*stride_l + :] + table[ids[b,l]]  (xattn_gpt.py:103-105,110-114); out-of-range
+ * ids set *err_flag (device int) to 1 -- the reference raises IndexError there. */
+int vima_add_pos_embed(vima_ctx*, const float* tok, int64_t stride_b, int64_t stride_l, const int64_t* ids, const float* table, int n_pos,
+                       int B, int L, int E, float* out_f32, void* hi, void* lo, int ld16, int dtype, int* err_flag, void* stream);
+/* vima_policy.py:180-233: prompt gather driven by a (kind, index) map per (b, position), see misc.cu. */
+int vima_gather_prompt(vima_ctx*, const int32_t* kind, const int32_t* index, const int64_t* word_ids, const float* word_table,
+                       const float* img_emb, const uint8_t* img_mask, int B, int Lp, int D, float* out, uint8_t* mask_out, void* stream);
+
+/* ---- object-encoder front end ---------------------------------------------------------------------------------
+ * preprocess.py:23-43 + vit.py:151-157,172: uint8 crops (N,3,H,W) -> normalised patch rows (hi, lo) [N*(H/P)*(W/P), ld16]. */
+int vima_patchify(vima_ctx*, const uint8_t* img, int64_t N, int H, int W, int P, void* hi, void* lo, int ld16, int dtype, void* stream);
+/* vit.py:173-179: tokens[n,0] = cls + pos[0]; tokens[n,1+p] = patch_out[n*(S-1)+p] + pos[1+p]. */
+int vima_vit_tokens(vima_ctx*, const float* patch_out, const float* cls, const float* pos, int64_t N, int S, int W, float* out, void* stream);
+/* obj_encoder.py:79-85 */
+int vima_bbox_norm(vima_ctx*, const int64_t* bbox, int64_t n, float* out, void* stream);
+/* vima_policy.py:253-256: end-effector embedding columns of the obs-fusion operand. */
+int vima_fill_ee(vima_ctx*, const int64_t* ee, const float* table, int64_t n_te, int Q, void* hi, void* lo, int ld16, int col0, int n_pad,
+                 int dtype, void* stream);
+/* preprocess.py:28 range check: *out_max = max(*out_max, max(x)) (device int). */
+int vima_max_u8(vima_ctx*, const uint8_t* x, int64_t n, int* out_max, void* stream);
+
+/* ---- action heads -------------------------------------------------------------------------------------------- */
+/* vima_policy.py:301-322: out[i,c] = float(idx[i,c]) / bins[c] */
+int vima_action_scale(vima_ctx*, const int64_t* idx, int64_t n, int width, const float* bins_dev, float* out, void* stream);
+/* dists.py:20-28: per head log-softmax normalised logits and mode (first argmax of probs). head_off: DEVICE int[n_heads+1]. */
+int vima_head_select(vima_ctx*, const float* logits, int B, int n_heads, const int32_t* head_off_dev, float* logits_norm, int64_t* modes,
+                     void* stream);
+
+#pragma GCC visibility pop
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIMA_B200_H */

@@ -1,0 +1,313 @@
+// C ABI of libvima_b200.so (see include/vima_b200.h).  Thin: validates arguments, builds TMA tensor maps and
+// launch configurations, and forwards to the kernels.  No host synchronisation anywhere.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/vima_b200.h"
+#include "gemm_tc.cuh"
+#include "kernels.h"
+
+using namespace vima;
+
+struct vima_ctx {
+  int device;
+  int sm_count;
+  int max_smem_optin;
+  long long launches;
+  char err[512];
+  void* encode_tiled;  // cuTensorMapEncodeTiled
+  bool gemm_attr_set;
+};
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int fail(vima_ctx* c, int code, const char* fmt, ...) {
+  if (c) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(c->err, sizeof(c->err), fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+static int cuda_fail(vima_ctx* c, cudaError_t e, const char* what) {
+  return fail(c, VIMA_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+#define CHECK_CTX(c)                  \
+  if (!(c)) return VIMA_E_INVALID;    \
+  {                                   \
+    cudaError_t e_ = cudaSetDevice((c)->device); \
+    if (e_ != cudaSuccess) return cuda_fail((c), e_, "cudaSetDevice"); \
+  }
+#define LAUNCHED(c, expr, name)                          \
+  {                                                      \
+    cudaError_t e_ = (expr);                             \
+    if (e_ != cudaSuccess) return cuda_fail((c), e_, name); \
+    (c)->launches++;                                     \
+    return VIMA_OK;                                      \
+  }
+
+extern "C" {
+
+int vima_abi_version(void) { return VIMA_B200_ABI_VERSION; }
+
+int vima_create(vima_ctx** out, int device) {
+  if (!out) return VIMA_E_INVALID;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return VIMA_E_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return VIMA_E_CUDA;
+  if (prop.major != 10) return VIMA_E_UNSUPPORTED;  // sm_100a code only; there is no fallback path
+  vima_ctx* c = new vima_ctx();
+  memset(c, 0, sizeof(*c));
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  if (cudaSetDevice(device) != cudaSuccess) { delete c; return VIMA_E_CUDA; }
+  cudaFree(0);
+  cudaDriverEntryPointQueryResult q;
+  void* fn = nullptr;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || fn == nullptr) {
+    delete c;
+    return VIMA_E_CUDA;
+  }
+  c->encode_tiled = fn;
+  *out = c;
+  return VIMA_OK;
+}
+
+void vima_destroy(vima_ctx* c) { delete c; }
+const char* vima_last_error(vima_ctx* c) { return c ? c->err : "null context"; }
+int vima_sm_count(vima_ctx* c) { return c ? c->sm_count : 0; }
+int64_t vima_launch_count(vima_ctx* c) { return c ? c->launches : 0; }
+
+int vima_split_f32(vima_ctx* c, const float* x, int64_t rows, int cols, int ldx, void* hi, void* lo, int ld16, int pad_cols, float scale,
+                   int dtype, void* stream) {
+  CHECK_CTX(c);
+  if (!x || !hi || pad_cols < cols || pad_cols > ld16) return fail(c, VIMA_E_INVALID, "split_f32: bad arguments");
+  LAUNCHED(c, launch_split(x, rows, cols, ldx, (unsigned short*)hi, (unsigned short*)lo, ld16, pad_cols, scale, dtype, (cudaStream_t)stream),
+           "split_f32");
+}
+
+int vima_pack_weight(vima_ctx* c, const float* w, int n, int k, int transposed, int ldw, void* hi, void* lo, int ld16, float scale, int dtype,
+                     void* stream) {
+  CHECK_CTX(c);
+  if (!w || !hi || ld16 < k || (ld16 & 7)) return fail(c, VIMA_E_INVALID, "pack_weight: ld16 must be >= k and a multiple of 8");
+  LAUNCHED(c, launch_pack_weight(w, n, k, transposed, ldw, (unsigned short*)hi, (unsigned short*)lo, ld16, scale, dtype, (cudaStream_t)stream),
+           "pack_weight");
+}
+
+static int choose_block_n(int N, int glu) {
+  const int step = glu ? 64 : 32;
+  int best = step, best_pad = 1 << 30;
+  for (int bn = step; bn <= 256; bn += step) {
+    const int padded = ((N + bn - 1) / bn) * bn;
+    if (padded < best_pad || (padded == best_pad && bn > best)) { best = bn; best_pad = padded; }
+  }
+  return best;
+}
+int vima_glu_block_n(int n_out) { return choose_block_n(2 * n_out, 1); }
+
+static int make_tmap(vima_ctx* c, CUtensorMap* tm, const void* base, int dtype, int rows, int cols, int ld, int box_rows) {
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)GEMM_BK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapDataType dt = dtype == DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = ((PFN_encodeTiled)c->encode_tiled)(tm, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(c, VIMA_E_CUDA, "cuTensorMapEncodeTiled failed (%d): rows %d cols %d ld %d box %d", (int)r, rows, cols, ld, box_rows);
+  return VIMA_OK;
+}
+
+int vima_gemm(vima_ctx* c, const vima_gemm_desc* d, void* stream) {
+  CHECK_CTX(c);
+  if (!d || !d->a_hi || !d->b_hi) return fail(c, VIMA_E_INVALID, "gemm: null operand");
+  if (d->M <= 0 || d->N <= 0 || d->K <= 0) return fail(c, VIMA_E_INVALID, "gemm: empty problem");
+  if ((d->lda & 7) || (d->ldb & 7) || ((uintptr_t)d->a_hi & 15) || ((uintptr_t)d->b_hi & 15))
+    return fail(c, VIMA_E_INVALID, "gemm: operands need 16-byte aligned bases and ld %% 8 == 0 (lda %d ldb %d)", d->lda, d->ldb);
+  if ((d->a_lo == nullptr) != (d->b_lo == nullptr)) return fail(c, VIMA_E_INVALID, "gemm: a_lo and b_lo must both be set or both be null");
+  if (d->lda < d->K || d->ldb < d->K) return fail(c, VIMA_E_INVALID, "gemm: leading dimension smaller than K");
+  int bn = d->block_n > 0 ? d->block_n : choose_block_n(d->N, d->glu);
+  if (bn > 256 || (bn % (d->glu ? 64 : 32))) return fail(c, VIMA_E_INVALID, "gemm: bad block_n %d", bn);
+  if (d->glu && (d->N % bn)) return fail(c, VIMA_E_INVALID, "gemm: GLU needs N %% block_n == 0");
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  const int split = d->a_lo != nullptr;
+  int rc;
+  if ((rc = make_tmap(c, &p.tm_a_hi, d->a_hi, d->dtype, d->M, d->K, d->lda, GEMM_BM))) return rc;
+  if ((rc = make_tmap(c, &p.tm_b_hi, d->b_hi, d->dtype, d->N, d->K, d->ldb, bn))) return rc;
+  if (split) {
+    if ((rc = make_tmap(c, &p.tm_a_lo, d->a_lo, d->dtype, d->M, d->K, d->lda, GEMM_BM))) return rc;
+    if ((rc = make_tmap(c, &p.tm_b_lo, d->b_lo, d->dtype, d->N, d->K, d->ldb, bn))) return rc;
+  }
+  p.M = d->M; p.N = d->N; p.K = d->K;
+  p.block_n = bn;
+  p.split = split;
+  p.dtype = d->dtype;
+  p.glu = d->glu;
+  p.act = d->act;
+  p.acc_scale = d->acc_scale == 0.f ? 1.f : d->acc_scale;
+  p.bias = d->bias;
+  p.mul = d->mul; p.ld_mul = d->ld_mul;
+  p.residual = d->residual; p.ld_res = d->ld_res;
+  p.out_f32 = d->out_f32; p.ld_o32 = d->ld_o32;
+  p.out_hi = (unsigned short*)d->out_hi; p.out_lo = (unsigned short*)d->out_lo; p.ld_o16 = d->ld_o16;
+
+  const size_t stage = (size_t)(GEMM_A_TILE_BYTES + bn * 128) * (split ? 2 : 1);
+  const size_t fixed = gemm_smem_bytes(bn, split, 0);
+  int n_stages = (int)(((size_t)c->max_smem_optin - fixed) / stage);
+  if (n_stages > GEMM_MAX_STAGES) n_stages = GEMM_MAX_STAGES;
+  if (n_stages < 2) return fail(c, VIMA_E_UNSUPPORTED, "gemm: not enough shared memory for 2 stages");
+  p.n_stages = n_stages;
+  const size_t smem = gemm_smem_bytes(bn, split, n_stages);
+  if (!c->gemm_attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin);
+    if (e != cudaSuccess) return cuda_fail(c, e, "cudaFuncSetAttribute(gemm)");
+    c->gemm_attr_set = true;
+  }
+  const int tiles = ((d->M + GEMM_BM - 1) / GEMM_BM) * ((d->N + bn - 1) / bn);
+  const int grid = tiles < c->sm_count ? tiles : c->sm_count;
+  gemm_tc_kernel<<<grid, GEMM_THREADS, smem, (cudaStream_t)stream>>>(p);
+  LAUNCHED(c, cudaGetLastError(), "gemm_tc_kernel");
+}
+
+int vima_gemm_f32_grouped(vima_ctx* c, const vima_f32_gemm_group* groups_dev, int n_groups, int M, int max_n, int act, void* stream) {
+  CHECK_CTX(c);
+  static_assert(sizeof(vima_f32_gemm_group) == sizeof(SimtGemmGroup), "group layout");
+  if (!groups_dev) return fail(c, VIMA_E_INVALID, "gemm_f32_grouped: null groups");
+  LAUNCHED(c, launch_simt_gemm_grouped(reinterpret_cast<const SimtGemmGroup*>(groups_dev), n_groups, M, max_n, act, (cudaStream_t)stream),
+           "simt_gemm");
+}
+
+int vima_norm(vima_ctx* c, const vima_norm_desc* d, void* stream) {
+  CHECK_CTX(c);
+  if (!d || !d->x) return fail(c, VIMA_E_INVALID, "norm: null input");
+  if ((d->cols & 3) || d->cols > 1024 || d->cols <= 0) return fail(c, VIMA_E_INVALID, "norm: cols must be a multiple of 4, <= 1024 (got %d)", d->cols);
+  if ((d->ldx & 3) || (d->add && (d->ld_add & 3)) || (d->out_f32 && (d->ld_o32 & 3)) || (d->out2_f32 && (d->ld_o2 & 3)) || (d->out_hi && (d->ld_o16 & 3)))
+    return fail(c, VIMA_E_INVALID, "norm: leading dimensions must be multiples of 4");
+  NormParams p;
+  p.x = d->x; p.rows = d->rows; p.cols = d->cols; p.ldx = d->ldx;
+  p.add = d->add; p.ld_add = d->ld_add;
+  p.w = d->w; p.b = d->b; p.eps = d->eps; p.rms = d->rms;
+  p.w2 = d->w2; p.b2 = d->b2; p.eps2 = d->eps2;
+  p.out_f32 = d->out_f32; p.ld_o32 = d->ld_o32;
+  p.out2_f32 = d->out2_f32; p.ld_o2 = d->ld_o2;
+  p.out_hi = (unsigned short*)d->out_hi; p.out_lo = (unsigned short*)d->out_lo; p.ld_o16 = d->ld_o16;
+  p.dtype = d->dtype;
+  LAUNCHED(c, launch_norm(p, (cudaStream_t)stream), "norm");
+}
+
+int vima_attention(vima_ctx* c, const vima_attn_desc* d, void* stream) {
+  CHECK_CTX(c);
+  if (!d || !d->q_hi || !d->k_hi || !d->v_hi || !d->o_hi) return fail(c, VIMA_E_INVALID, "attention: null operand");
+  if (d->D != 32 && d->D != 64) return fail(c, VIMA_E_UNSUPPORTED, "attention: head_dim %d (32 and 64 are built)", d->D);
+  if ((d->ldq & 7) || (d->ldk & 7) || (d->ldv & 7) || (d->ldo & 1)) return fail(c, VIMA_E_INVALID, "attention: leading dimensions must be multiples of 8");
+  const bool split = d->q_lo != nullptr;
+  if (split != (d->k_lo != nullptr) || split != (d->v_lo != nullptr)) return fail(c, VIMA_E_INVALID, "attention: q/k/v lo parts must be all set or all null");
+  if (d->rel_bias && d->Lq != d->Lk) return fail(c, VIMA_E_INVALID, "attention: relative bias needs Lq == Lk");
+  if (d->Lk > 1024) return fail(c, VIMA_E_UNSUPPORTED, "attention: Lk %d exceeds the shared-memory resident design (1024)", d->Lk);
+  AttnParams p;
+  p.q_hi = (const unsigned short*)d->q_hi; p.q_lo = (const unsigned short*)d->q_lo; p.ldq = d->ldq;
+  p.k_hi = (const unsigned short*)d->k_hi; p.k_lo = (const unsigned short*)d->k_lo; p.ldk = d->ldk;
+  p.v_hi = (const unsigned short*)d->v_hi; p.v_lo = (const unsigned short*)d->v_lo; p.ldv = d->ldv;
+  p.key_mask = d->key_mask; p.rel_bias = d->rel_bias;
+  p.o_hi = (unsigned short*)d->o_hi; p.o_lo = (unsigned short*)d->o_lo; p.ldo = d->ldo;
+  p.B = d->B; p.H = d->H; p.Lq = d->Lq; p.Lk = d->Lk; p.D = d->D;
+  p.scale = d->scale; p.causal = d->causal; p.split = split; p.dtype = d->dtype;
+  LAUNCHED(c, launch_attention(p, (cudaStream_t)stream), "attention");
+}
+
+int vima_small_attention(vima_ctx* c, const float* qkv, int ld, int64_t N, int S, int H, int W, float scale, void* o_hi, void* o_lo, int ldo,
+                         float* o_f32, int dtype, void* stream) {
+  CHECK_CTX(c);
+  if (!qkv) return fail(c, VIMA_E_INVALID, "small_attention: null input");
+  SmallAttnParams p;
+  p.qkv = qkv; p.ld = ld; p.o_hi = (unsigned short*)o_hi; p.o_lo = (unsigned short*)o_lo; p.ldo = ldo; p.o_f32 = o_f32;
+  p.N = N; p.S = S; p.H = H; p.W = W; p.scale = scale; p.dtype = dtype;
+  LAUNCHED(c, launch_small_attention(p, (cudaStream_t)stream), "small_attention");
+}
+
+int vima_assemble_history(vima_ctx* c, const float* obs, const uint8_t* obs_mask, const float* action, int T, int B, int Q, int E, int La,
+                          float* tokens, uint8_t* masks_bl, int64_t* pos_bl, void* stream) {
+  CHECK_CTX(c);
+  if (!obs || !obs_mask || !tokens || !masks_bl || !pos_bl || (La > 0 && !action) || (E & 3))
+    return fail(c, VIMA_E_INVALID, "assemble_history: bad arguments");
+  if (La != T && La != T - 1) return fail(c, VIMA_E_INVALID, "assemble_history: need T-1 or T action tokens");
+  cudaError_t e = launch_assemble_history(obs, obs_mask, action, T, B, Q, E, La, tokens, masks_bl, (long long*)pos_bl, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(c, e, "assemble_history");
+  c->launches += 2;
+  return VIMA_OK;
+}
+
+int vima_mask_cumsum(vima_ctx* c, const uint8_t* mask, int B, int L, int64_t* pos, void* stream) {
+  CHECK_CTX(c);
+  LAUNCHED(c, launch_mask_cumsum(mask, B, L, (long long*)pos, (cudaStream_t)stream), "mask_cumsum");
+}
+
+int vima_add_pos_embed(vima_ctx* c, const float* tok, int64_t stride_b, int64_t stride_l, const int64_t* ids, const float* table, int n_pos, int B,
+                       int L, int E, float* out_f32, void* hi, void* lo, int ld16, int dtype, int* err_flag, void* stream) {
+  CHECK_CTX(c);
+  if ((E & 3) || (stride_b & 3) || (stride_l & 3) || (hi && (ld16 & 3))) return fail(c, VIMA_E_INVALID, "add_pos_embed: alignment");
+  LAUNCHED(c, launch_add_pos_embed(tok, stride_b, stride_l, (const long long*)ids, table, n_pos, B, L, E, out_f32, (unsigned short*)hi,
+                                   (unsigned short*)lo, ld16, dtype, err_flag, (cudaStream_t)stream),
+           "add_pos_embed");
+}
+
+int vima_gather_prompt(vima_ctx* c, const int32_t* kind, const int32_t* index, const int64_t* word_ids, const float* word_table,
+                       const float* img_emb, const uint8_t* img_mask, int B, int Lp, int D, float* out, uint8_t* mask_out, void* stream) {
+  CHECK_CTX(c);
+  if (D & 3) return fail(c, VIMA_E_INVALID, "gather_prompt: D %% 4");
+  LAUNCHED(c, launch_gather_prompt(kind, index, (const long long*)word_ids, word_table, img_emb, img_mask, B, Lp, D, out, mask_out,
+                                   (cudaStream_t)stream),
+           "gather_prompt");
+}
+
+int vima_patchify(vima_ctx* c, const uint8_t* img, int64_t N, int H, int W, int P, void* hi, void* lo, int ld16, int dtype, void* stream) {
+  CHECK_CTX(c);
+  if ((P & 3) || (H % P) || (W % P) || (ld16 & 3) || ld16 < 3 * P * P) return fail(c, VIMA_E_INVALID, "patchify: bad geometry");
+  LAUNCHED(c, launch_patchify(img, N, H, W, P, (unsigned short*)hi, (unsigned short*)lo, ld16, dtype, (cudaStream_t)stream), "patchify");
+}
+
+int vima_vit_tokens(vima_ctx* c, const float* patch_out, const float* cls, const float* pos, int64_t N, int S, int W, float* out, void* stream) {
+  CHECK_CTX(c);
+  if (W & 3) return fail(c, VIMA_E_INVALID, "vit_tokens: W %% 4");
+  LAUNCHED(c, launch_vit_tokens(patch_out, cls, pos, N, S, W, out, (cudaStream_t)stream), "vit_tokens");
+}
+
+int vima_bbox_norm(vima_ctx* c, const int64_t* bbox, int64_t n, float* out, void* stream) {
+  CHECK_CTX(c);
+  LAUNCHED(c, launch_bbox_norm((const long long*)bbox, n, out, (cudaStream_t)stream), "bbox_norm");
+}
+
+int vima_fill_ee(vima_ctx* c, const int64_t* ee, const float* table, int64_t n_te, int Q, void* hi, void* lo, int ld16, int col0, int n_pad,
+                 int dtype, void* stream) {
+  CHECK_CTX(c);
+  LAUNCHED(c, launch_fill_ee((const long long*)ee, table, n_te, Q, (unsigned short*)hi, (unsigned short*)lo, ld16, col0, n_pad, dtype,
+                             (cudaStream_t)stream),
+           "fill_ee");
+}
+
+int vima_max_u8(vima_ctx* c, const uint8_t* x, int64_t n, int* out_max, void* stream) {
+  CHECK_CTX(c);
+  LAUNCHED(c, launch_max_u8(x, n, out_max, (cudaStream_t)stream), "max_u8");
+}
+
+int vima_action_scale(vima_ctx* c, const int64_t* idx, int64_t n, int width, const float* bins_dev, float* out, void* stream) {
+  CHECK_CTX(c);
+  LAUNCHED(c, launch_action_scale((const long long*)idx, n, width, bins_dev, out, (cudaStream_t)stream), "action_scale");
+}
+
+int vima_head_select(vima_ctx* c, const float* logits, int B, int n_heads, const int32_t* head_off_dev, float* logits_norm, int64_t* modes,
+                     void* stream) {
+  CHECK_CTX(c);
+  LAUNCHED(c, launch_head_select(logits, B, n_heads, head_off_dev, logits_norm, (long long*)modes, (cudaStream_t)stream), "head_select");
+}
+
+}  // extern "C"

@@ -1,0 +1,335 @@
+// Fused masked attention for the VIMA decoder / T5 encoder (head_dim 32 or 64, sequences <= 512).
+//
+//   S = scale * Q K^T (+ T5 relative bias) ; causal: S[i][j>i] = -1e4 (the reference's soft mask,
+//   components.py:61-63) ; S += (key_mask ? 0 : finfo(fp32).min) ; P = softmax(S) ; O = P V
+//
+// One CTA per (batch, head): K and V^T of that head stay in shared memory, each warp streams 16-query-row
+// blocks with an online fp32 softmax (warp-shuffle row reductions) and mma.sync m16n8k16 tensor-core products.
+// In split mode Q,K,V,P are (hi,lo) 16-bit pairs and every product is hi*hi + lo*hi + hi*lo, which keeps the
+// logits and the PV sum at ~fp32 accuracy (the reference computes both in fp32).  Scores never touch HBM:
+// the reference materialises a 1.7 GB fp32 score tensor per layer at B=256.
+#include "kernels.h"
+
+namespace vima {
+
+constexpr float FP32_MIN = -3.4028234663852886e38f;
+constexpr float LOG2E = 1.4426950408889634f;
+
+template <int DT>
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if constexpr (DT == DT_F16) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  } else {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  }
+}
+
+template <int DT>
+__device__ __forceinline__ void pack_split(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  unsigned short h0, l0, h1, l1;
+  split16<DT>(x0, h0, l0);
+  split16<DT>(x1, h1, l1);
+  hi = (uint32_t)h0 | ((uint32_t)h1 << 16);
+  lo = (uint32_t)l0 | ((uint32_t)l1 << 16);
+}
+
+template <int D, int DT, bool SPLIT>
+__global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
+  constexpr int KS = D / 16;   // k-steps over head_dim for Q K^T
+  constexpr int ND = D / 8;    // n-tiles over head_dim for P V
+  constexpr int KROW = D + 8;  // padded smem row (halfs) -> conflict-free 32-bit fragment loads
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int Lk = p.Lk, Lq = p.Lq;
+  const int Lk_pad = (Lk + 63) & ~63;
+  const int VROW = Lk_pad + 8;
+  unsigned short* Ks_hi = reinterpret_cast<unsigned short*>(smem);
+  unsigned short* Ks_lo = Ks_hi + (SPLIT ? Lk_pad * KROW : 0);
+  unsigned short* Vt_hi = Ks_lo + Lk_pad * KROW;
+  unsigned short* Vt_lo = Vt_hi + (SPLIT ? D * VROW : 0);
+  float* maskadd = reinterpret_cast<float*>(Vt_lo + D * VROW);
+  float* sbias = maskadd + Lk_pad;  // [2*Lk-1] when rel_bias
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // ---- stage K (row-major) and V (transposed) of this (b, h) in shared memory ----
+  constexpr int CH = D / 8;  // 16-byte chunks per row
+  for (int idx = tid; idx < Lk_pad * CH; idx += 256) {
+    const int j = idx / CH, c = idx % CH;
+    uint4 kh = make_uint4(0, 0, 0, 0), kl = kh, vh = kh, vl = kh;
+    if (j < Lk) {
+      const size_t rk = (size_t)(b * Lk + j) * p.ldk + h * D + c * 8;
+      const size_t rv = (size_t)(b * Lk + j) * p.ldv + h * D + c * 8;
+      kh = __ldg(reinterpret_cast<const uint4*>(p.k_hi + rk));
+      vh = __ldg(reinterpret_cast<const uint4*>(p.v_hi + rv));
+      if (SPLIT) {
+        kl = __ldg(reinterpret_cast<const uint4*>(p.k_lo + rk));
+        vl = __ldg(reinterpret_cast<const uint4*>(p.v_lo + rv));
+      }
+    }
+    *reinterpret_cast<uint4*>(Ks_hi + j * KROW + c * 8) = kh;
+    if (SPLIT) *reinterpret_cast<uint4*>(Ks_lo + j * KROW + c * 8) = kl;
+    const unsigned short* vhs = reinterpret_cast<const unsigned short*>(&vh);
+    const unsigned short* vls = reinterpret_cast<const unsigned short*>(&vl);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      Vt_hi[(c * 8 + e) * VROW + j] = vhs[e];
+      if (SPLIT) Vt_lo[(c * 8 + e) * VROW + j] = vls[e];
+    }
+  }
+  for (int j = tid; j < Lk_pad; j += 256) {
+    float m = -INFINITY;  // beyond the sequence: excluded
+    if (j < Lk) m = (p.key_mask == nullptr || p.key_mask[(size_t)b * Lk + j]) ? 0.f : FP32_MIN;
+    maskadd[j] = m;
+  }
+  if (p.rel_bias)
+    for (int j = tid; j < 2 * Lk - 1; j += 256) sbias[j] = __ldg(p.rel_bias + (size_t)h * (2 * Lk - 1) + j);
+  __syncthreads();
+
+  const int g = lane >> 2, t = lane & 3;
+  const int n_qb = (Lq + 15) / 16;
+  const int n_kt = Lk_pad / 64;
+  for (int qb = warp; qb < n_qb; qb += 8) {
+    const int r0 = qb * 16 + g, r1 = r0 + 8;
+    uint32_t qh[KS][4], ql[KS][4];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int r = (e & 1) ? r1 : r0;
+        const int c = ks * 16 + 2 * t + ((e & 2) ? 8 : 0);
+        uint32_t vh = 0, vl = 0;
+        if (r < Lq) {
+          const size_t off = (size_t)(b * Lq + r) * p.ldq + h * D + c;
+          vh = __ldg(reinterpret_cast<const uint32_t*>(p.q_hi + off));
+          if (SPLIT) vl = __ldg(reinterpret_cast<const uint32_t*>(p.q_lo + off));
+        }
+        qh[ks][e] = vh;
+        ql[ks][e] = vl;
+      }
+    }
+    float o[ND][4];
+#pragma unroll
+    for (int n = 0; n < ND; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+    float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
+
+    for (int kt = 0; kt < n_kt; ++kt) {
+      float s[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+        const int key = kt * 64 + nt * 8 + g;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          const unsigned short* kp = Ks_hi + key * KROW + ks * 16 + 2 * t;
+          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kp);
+          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kp + 8);
+          mma16816<DT>(s[nt], qh[ks], b0, b1);
+          if (SPLIT) {
+            mma16816<DT>(s[nt], ql[ks], b0, b1);
+            const unsigned short* kq = Ks_lo + key * KROW + ks * 16 + 2 * t;
+            mma16816<DT>(s[nt], qh[ks], *reinterpret_cast<const uint32_t*>(kq), *reinterpret_cast<const uint32_t*>(kq + 8));
+          }
+        }
+      }
+      // ---- scale, bias, soft causal mask, key mask; row max ----
+      float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = kt * 64 + nt * 8 + 2 * t + (e & 1);
+          const int i = (e & 2) ? r1 : r0;
+          float x = s[nt][e] * p.scale;
+          if (p.rel_bias && j < Lk) x += sbias[j - min(i, Lq - 1) + Lk - 1];
+          if (p.causal && j > i) x = -1e4f;
+          x += maskadd[j];
+          s[nt][e] = x;
+          mx[e >> 1] = fmaxf(mx[e >> 1], x);
+        }
+      }
+      float corr[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+        const float m_new = fmaxf(mrow[r], mx[r]);
+        corr[r] = exp2f((mrow[r] - m_new) * LOG2E);
+        mrow[r] = m_new;
+        lrow[r] *= corr[r];
+      }
+      float ps[2] = {0.f, 0.f};
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float pv = exp2f((s[nt][e] - mrow[e >> 1]) * LOG2E);
+          s[nt][e] = pv;
+          ps[e >> 1] += pv;
+        }
+      }
+      lrow[0] += ps[0];
+      lrow[1] += ps[1];
+#pragma unroll
+      for (int n = 0; n < ND; ++n) {
+        o[n][0] *= corr[0]; o[n][1] *= corr[0];
+        o[n][2] *= corr[1]; o[n][3] *= corr[1];
+      }
+      // ---- O += P V ----
+#pragma unroll
+      for (int k2 = 0; k2 < 4; ++k2) {
+        uint32_t ph[4], pl[4];
+        pack_split<DT>(s[2 * k2][0], s[2 * k2][1], ph[0], pl[0]);
+        pack_split<DT>(s[2 * k2][2], s[2 * k2][3], ph[1], pl[1]);
+        pack_split<DT>(s[2 * k2 + 1][0], s[2 * k2 + 1][1], ph[2], pl[2]);
+        pack_split<DT>(s[2 * k2 + 1][2], s[2 * k2 + 1][3], ph[3], pl[3]);
+        const int k0 = kt * 64 + k2 * 16 + 2 * t;
+#pragma unroll
+        for (int n = 0; n < ND; ++n) {
+          const unsigned short* vp = Vt_hi + (n * 8 + g) * VROW + k0;
+          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vp);
+          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(vp + 8);
+          mma16816<DT>(o[n], ph, b0, b1);
+          if (SPLIT) {
+            mma16816<DT>(o[n], pl, b0, b1);
+            const unsigned short* vq = Vt_lo + (n * 8 + g) * VROW + k0;
+            mma16816<DT>(o[n], ph, *reinterpret_cast<const uint32_t*>(vq), *reinterpret_cast<const uint32_t*>(vq + 8));
+          }
+        }
+      }
+      // Every later key tile is causally masked for all 16 rows: its weights are exp(-1e4 - m), exactly 0 in
+      // fp32 once m > -1e4 + 104, so stopping here is bit-identical to the reference's full-width softmax.
+      if (p.causal && (kt + 1) * 64 > qb * 16 + 15) {
+        const bool done = (mrow[0] > -9000.f) && (mrow[1] > -9000.f);
+        if (__all_sync(0xffffffffu, done)) break;
+      }
+    }
+    // row sums live in the 4 lanes of a quad
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      lrow[r] += __shfl_xor_sync(0xffffffffu, lrow[r], 1);
+      lrow[r] += __shfl_xor_sync(0xffffffffu, lrow[r], 2);
+    }
+    const float inv0 = 1.0f / lrow[0], inv1 = 1.0f / lrow[1];
+#pragma unroll
+    for (int n = 0; n < ND; ++n) {
+      const int c = h * D + n * 8 + 2 * t;
+      uint32_t hi, lo;
+      if (r0 < Lq) {
+        pack_split<DT>(o[n][0] * inv0, o[n][1] * inv0, hi, lo);
+        const size_t off = (size_t)(b * Lq + r0) * p.ldo + c;
+        *reinterpret_cast<uint32_t*>(p.o_hi + off) = hi;
+        if (p.o_lo) *reinterpret_cast<uint32_t*>(p.o_lo + off) = lo;
+      }
+      if (r1 < Lq) {
+        pack_split<DT>(o[n][2] * inv1, o[n][3] * inv1, hi, lo);
+        const size_t off = (size_t)(b * Lq + r1) * p.ldo + c;
+        *reinterpret_cast<uint32_t*>(p.o_hi + off) = hi;
+        if (p.o_lo) *reinterpret_cast<uint32_t*>(p.o_lo + off) = lo;
+      }
+    }
+  }
+}
+
+template <int D, int DT, bool SPLIT>
+static cudaError_t launch_attn_t(const AttnParams& p, cudaStream_t stream) {
+  const int Lk_pad = (p.Lk + 63) & ~63;
+  const size_t parts = SPLIT ? 2 : 1;
+  size_t smem = parts * (size_t)Lk_pad * (D + 8) * 2 + parts * (size_t)D * (Lk_pad + 8) * 2 + (size_t)Lk_pad * 4;
+  if (p.rel_bias) smem += (size_t)(2 * p.Lk) * 4;
+  auto kern = attention_kernel<D, DT, SPLIT>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  dim3 grid(p.H, p.B);
+  kern<<<grid, 256, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream) {
+  if (p.B == 0 || p.Lq == 0) return cudaSuccess;
+  const bool sp = p.split != 0;
+  if (p.D == 32) {
+    if (p.dtype == DT_F16) return sp ? launch_attn_t<32, DT_F16, true>(p, stream) : launch_attn_t<32, DT_F16, false>(p, stream);
+    return sp ? launch_attn_t<32, DT_BF16, true>(p, stream) : launch_attn_t<32, DT_BF16, false>(p, stream);
+  }
+  if (p.D == 64) {
+    if (p.dtype == DT_F16) return sp ? launch_attn_t<64, DT_F16, true>(p, stream) : launch_attn_t<64, DT_F16, false>(p, stream);
+    return sp ? launch_attn_t<64, DT_BF16, true>(p, stream) : launch_attn_t<64, DT_BF16, false>(p, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Tiny-sequence attention in fp32 (ViT: 5 tokens per crop).  One warp per (crop, head); lane = head_dim index
+// (head_dim must be 32).  qkv carries the in_proj bias already.  Everything stays in registers.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int SMALL_S_MAX = 16;
+
+template <int DT>
+__global__ void __launch_bounds__(256) small_attention_kernel(const SmallAttnParams p) {
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= p.N * p.H) return;
+  const long long n = w / p.H;
+  const int h = (int)(w % p.H);
+  const int S = p.S;
+  float q[SMALL_S_MAX], k[SMALL_S_MAX], v[SMALL_S_MAX];
+#pragma unroll
+  for (int s = 0; s < SMALL_S_MAX; ++s) {
+    if (s < S) {
+      const float* row = p.qkv + (size_t)(n * S + s) * p.ld + h * 32 + lane;
+      q[s] = __ldg(row);
+      k[s] = __ldg(row + p.W);
+      v[s] = __ldg(row + 2 * p.W);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < SMALL_S_MAX; ++i) {
+    if (i < S) {
+      float sc[SMALL_S_MAX];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < SMALL_S_MAX; ++j) {
+        if (j < S) {
+          sc[j] = warp_sum(q[i] * k[j]) * p.scale;
+          mx = fmaxf(mx, sc[j]);
+        }
+      }
+      float den = 0.f, acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < SMALL_S_MAX; ++j) {
+        if (j < S) {
+          const float e = expf(sc[j] - mx);
+          den += e;
+          acc += e * v[j];
+        }
+      }
+      const float outv = acc / den;
+      const size_t off = (size_t)(n * S + i) * p.ldo + h * 32 + lane;
+      if (p.o_f32) p.o_f32[off] = outv;
+      if (p.o_hi) {
+        unsigned short hi, lo;
+        split16<DT>(outv, hi, lo);
+        p.o_hi[off] = hi;
+        if (p.o_lo) p.o_lo[off] = lo;
+      }
+    }
+  }
+}
+
+cudaError_t launch_small_attention(const SmallAttnParams& p, cudaStream_t stream) {
+  if (p.N == 0) return cudaSuccess;
+  if (p.S > SMALL_S_MAX || p.W != p.H * 32) return cudaErrorInvalidValue;
+  const long long warps = p.N * p.H;
+  const long long blocks = (warps + 7) / 8;
+  if (p.dtype == DT_BF16)
+    small_attention_kernel<DT_BF16><<<(unsigned)blocks, 256, 0, stream>>>(p);
+  else
+    small_attention_kernel<DT_F16><<<(unsigned)blocks, 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace vima

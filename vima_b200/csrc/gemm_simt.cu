@@ -1,0 +1,61 @@
+// Exact-fp32 grouped GEMM on CUDA cores for the path's tiny / odd-shaped layers (bbox MLP K=4, action embedding
+// K=2|4, the 12 action-head MLPs with N=50|100, M = episodes).  y[M,n] = act(x[M,k] * w[n,k]^T + b), one group
+// per blockIdx.z.  These layers are <0.1 % of the step's FLOPs; keeping them in fp32 FFMA means the action
+// logits carry no tensor-core rounding of their own.
+#include "kernels.h"
+
+namespace vima {
+
+constexpr int ST = 64;   // tile edge
+constexpr int SK = 16;   // k step
+
+__global__ void __launch_bounds__(256) simt_gemm_kernel(const SimtGemmGroup* __restrict__ groups, int M, int act) {
+  const SimtGemmGroup g = groups[blockIdx.z];
+  const int n0 = blockIdx.x * ST, m0 = blockIdx.y * ST;
+  if (n0 >= g.n) return;
+  __shared__ float xs[SK][ST + 4];
+  __shared__ float ws[SK][ST + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, 4 x 4 outputs each
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < g.k; k0 += SK) {
+    for (int i = threadIdx.x; i < ST * SK; i += 256) {
+      const int r = i / SK, kk = i % SK;
+      const int m = m0 + r, n = n0 + r, k = k0 + kk;
+      xs[kk][r] = (m < M && k < g.k) ? __ldg(g.x + (size_t)m * g.ldx + k) : 0.f;
+      ws[kk][r] = (n < g.n && k < g.k) ? __ldg(g.w + (size_t)n * g.ldw + k) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < SK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = xs[kk][ty * 4 + i]; b[i] = ws[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= g.n) continue;
+      float v = acc[i][j] + (g.b ? __ldg(g.b + n) : 0.f);
+      g.y[(size_t)m * g.ldy + n] = apply_act(act, v);
+    }
+  }
+}
+
+cudaError_t launch_simt_gemm_grouped(const SimtGemmGroup* groups_dev, int n_groups, int M, int max_n, int act, cudaStream_t stream) {
+  if (M == 0 || n_groups == 0) return cudaSuccess;
+  dim3 grid((max_n + ST - 1) / ST, (M + ST - 1) / ST, n_groups);
+  simt_gemm_kernel<<<grid, 256, 0, stream>>>(groups_dev, M, act);
+  return cudaGetLastError();
+}
+
+}  // namespace vima

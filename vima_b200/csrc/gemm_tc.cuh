@@ -1,0 +1,250 @@
+// tcgen05 GEMM for sm_100a:  C[M,N] = epilogue( A[M,K] * B[N,K]^T )
+//
+//  * A (activations) and B (packed weights) are K-major 16-bit operands (fp16 or bf16), optionally as (hi, lo)
+//    pairs: in split mode the kernel accumulates A_hi*B_hi + A_lo*B_hi + A_hi*B_lo in the SAME fp32 TMEM
+//    accumulator, which restores ~fp32 products (see DESIGN.md "operand precision").
+//  * Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
+//    warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM -> registers -> smem transpose -> coalesced global).
+//  * smem ring of `n_stages` stages {A_hi,[A_lo],B_hi,[B_lo]} in the 128-byte swizzled K-major layout that TMA
+//    writes and the UMMA descriptors read; two 256-column fp32 accumulators in TMEM so the epilogue of tile i
+//    overlaps the main loop of tile i+1.
+//  * Epilogue: acc*scale + bias -> activation -> (GLU pair product) -> *mul -> +residual -> fp32 and/or (hi,lo).
+#pragma once
+#include "common.cuh"
+
+namespace vima {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;                       // 64 x 2 B = 128 B = one swizzle row
+constexpr int GEMM_A_TILE_BYTES = GEMM_BM * 128;  // 16 KB
+constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_MAX_STAGES = 8;
+constexpr int GEMM_STAGING_BYTES = 4 * 32 * 33 * 4;  // per-epilogue-warp 32x33 fp32 transpose buffers
+constexpr int GEMM_TMEM_COLS = 512;
+
+struct alignas(64) GemmParams {
+  CUtensorMap tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo;
+  int M, N, K;      // N = accumulator columns (2x the output columns in GLU mode)
+  int block_n;      // multiple of 32 (64 in GLU mode), <= 256
+  int n_stages;
+  int split;        // 0: hi*hi only, 1: three-term split product
+  int dtype;        // DT_F16 / DT_BF16 (operand and 16-bit output format)
+  int glu;          // 1: out[:, t*bn/2 + c] = act(acc[c]+bias[c]) * (acc[bn/2+c]+bias[bn/2+c]) per tile t
+  int act;
+  float acc_scale;  // un-scale of pre-scaled packed weights (power of two)
+  const float* bias;      // [N] in accumulator-column order, or null
+  const float* mul;       // fp32 [M, Nout] multiplier, or null
+  int ld_mul;
+  const float* residual;  // fp32 [M, Nout], or null
+  int ld_res;
+  float* out_f32;         // or null
+  int ld_o32;
+  unsigned short* out_hi; // 16-bit outputs (operand format), or null
+  unsigned short* out_lo;
+  int ld_o16;
+};
+
+__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
+  // start address [0,14) (>>4) | LBO [16,30) (ignored for swizzled K-major; 1) | SBO [32,46) = 8 rows * 128 B
+  // | version [46,48) = 1 (sm_100) | layout type [61,64) = 2 (SWIZZLE_128B)
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages][staging][bias 2x256 f32][barriers][tmem ptr]
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int BN = p.block_n;
+  const int b_tile_bytes = BN * 128;
+  const int n_parts = p.split ? 2 : 1;
+  const int stage_bytes = (GEMM_A_TILE_BYTES + b_tile_bytes) * n_parts;
+  uint8_t* stages = smem;
+  float* staging = (float*)(smem + (size_t)p.n_stages * stage_bytes);
+  float* sbias = staging + GEMM_STAGING_BYTES / 4;  // [2][256]
+  uint64_t* bars = (uint64_t*)(sbias + 512);
+  uint64_t* full_bar = bars;                          // [n_stages]
+  uint64_t* empty_bar = bars + GEMM_MAX_STAGES;       // [n_stages]
+  uint64_t* tmem_full = bars + 2 * GEMM_MAX_STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;               // [2]
+  uint32_t* tmem_ptr_smem = (uint32_t*)(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tm_a_hi);
+    tma_prefetch_desc(&p.tm_b_hi);
+    if (p.split) {
+      tma_prefetch_desc(&p.tm_a_lo);
+      tma_prefetch_desc(&p.tm_b_lo);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.n_stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<GEMM_TMEM_COLS>(tmem_ptr_smem);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * GEMM_BM;
+        const int n0 = (tile % tiles_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = stages + (size_t)stage * stage_bytes;
+          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+          const int k0 = kb * GEMM_BK;
+          tma_load_2d(st, &p.tm_a_hi, &full_bar[stage], k0, m0);
+          uint8_t* sb = st + GEMM_A_TILE_BYTES * n_parts;
+          tma_load_2d(sb, &p.tm_b_hi, &full_bar[stage], k0, n0);
+          if (p.split) {
+            tma_load_2d(st + GEMM_A_TILE_BYTES, &p.tm_a_lo, &full_bar[stage], k0, m0);
+            tma_load_2d(sb + b_tile_bytes, &p.tm_b_lo, &full_bar[stage], k0, n0);
+          }
+          if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t fmt = (p.dtype == DT_BF16) ? 1u : 0u;
+      // c_format F32 (bit 4) | a_format [7,10) | b_format [10,13) | K-major A,B | N>>3 [17,23) | M>>4 [24,29)
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int ab = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[ab], aphase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(ab * 256);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t a_hi = smem_u32(stages + (size_t)stage * stage_bytes);
+          const uint32_t b_hi = a_hi + GEMM_A_TILE_BYTES * n_parts;
+          const uint64_t da_hi = make_sw128_kmajor_desc(a_hi);
+          const uint64_t db_hi = make_sw128_kmajor_desc(b_hi);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k)  // +32 B per K=16 step inside the 128 B swizzle row
+            umma_f16(d_tmem, da_hi + 2 * k, db_hi + 2 * k, idesc, (kb | k) != 0);
+          if (p.split) {
+            const uint64_t da_lo = make_sw128_kmajor_desc(a_hi + GEMM_A_TILE_BYTES);
+            const uint64_t db_lo = make_sw128_kmajor_desc(b_hi + b_tile_bytes);
+#pragma unroll
+            for (int k = 0; k < GEMM_BK / 16; ++k) umma_f16(d_tmem, da_lo + 2 * k, db_hi + 2 * k, idesc, 1u);
+#pragma unroll
+            for (int k = 0; k < GEMM_BK / 16; ++k) umma_f16(d_tmem, da_hi + 2 * k, db_lo + 2 * k, idesc, 1u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[ab]);  // accumulator complete -> epilogue
+        if (++ab == 2) { ab = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int we = warp - 4;  // == warp % 4 : TMEM lane quadrant
+    float* st = staging + we * (32 * 33);
+    const int et = threadIdx.x - 128;  // 0..127
+    const int n_out = p.glu ? p.N / 2 : p.N;
+    const int bn_out = p.glu ? BN / 2 : BN;
+    int ab = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / tiles_n) * GEMM_BM;
+      const int tn = tile % tiles_n;
+      const int n0 = tn * BN;
+      float* sb = sbias + ab * 256;
+      // bias tile -> smem (visible to the 4 epilogue warps after the named barrier)
+      for (int c = et; c < BN; c += 128) sb[c] = (p.bias != nullptr && n0 + c < p.N) ? __ldg(p.bias + n0 + c) : 0.f;
+      named_bar_sync(1, 128);
+      mbar_wait(&tmem_full[ab], aphase);
+      tcgen05_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(we * 32) << 16) + (uint32_t)(ab * 256);
+      const int row_base = m0 + we * 32;
+      for (int j = 0; j < bn_out; j += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_row + j, v);
+        float x[32];
+        if (p.glu) {
+          uint32_t g[32];
+          tmem_ld_32x32(t_row + bn_out + j, g);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float a = apply_act(p.act, __uint_as_float(v[i]) * p.acc_scale + sb[j + i]);
+            x[i] = a * (__uint_as_float(g[i]) * p.acc_scale + sb[bn_out + j + i]);
+          }
+        } else {
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = apply_act(p.act, __uint_as_float(v[i]) * p.acc_scale + sb[j + i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) st[lane * 33 + i] = x[i];
+        __syncwarp();
+        const int col = tn * bn_out + j + lane;
+        const bool col_ok = col < n_out;
+        const int rmax = min(32, p.M - row_base);
+#pragma unroll 4
+        for (int r = 0; r < rmax; ++r) {
+          float y = st[r * 33 + lane];
+          const size_t row = (size_t)(row_base + r);
+          if (col_ok) {
+            if (p.mul) y *= __ldg(p.mul + row * p.ld_mul + col);
+            if (p.residual) y += __ldg(p.residual + row * p.ld_res + col);
+            if (p.out_f32) p.out_f32[row * p.ld_o32 + col] = y;
+            if (p.out_hi) {
+              unsigned short hi, lo;
+              split16_rt(p.dtype, y, hi, lo);
+              p.out_hi[row * p.ld_o16 + col] = hi;
+              if (p.out_lo) p.out_lo[row * p.ld_o16 + col] = lo;
+            }
+          }
+        }
+        __syncwarp();
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[ab]);
+      if (++ab == 2) { ab = 0; aphase ^= 1; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc<GEMM_TMEM_COLS>(tmem_base);
+  }
+}
+
+inline size_t gemm_smem_bytes(int block_n, int split, int n_stages) {
+  const size_t stage = (size_t)(GEMM_A_TILE_BYTES + block_n * 128) * (split ? 2 : 1);
+  return 1024 /*align slack*/ + n_stages * stage + GEMM_STAGING_BYTES + 512 * 4 + (2 * GEMM_MAX_STAGES + 4) * 8 + 16;
+}
+
+}  // namespace vima

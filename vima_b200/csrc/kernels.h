@@ -1,0 +1,74 @@
+// Internal launch interface between the C-ABI layer (api.cu) and the kernel translation units.
+#pragma once
+#include "common.cuh"
+
+namespace vima {
+
+struct NormParams {
+  const float* x; long long rows; int cols; int ldx;
+  const float* add; int ld_add;       // optional: normalise (x + add)
+  const float* w; const float* b;     // first norm (w == null: no normalisation, passthrough/convert only)
+  float eps; int rms;                 // rms=1: T5 RMSNorm (no mean, no bias)
+  const float* w2; const float* b2; float eps2;  // optional chained LayerNorm on the first norm's output
+  float* out_f32; int ld_o32;         // output of the first norm (fp32), optional
+  float* out2_f32; int ld_o2;         // output of the second norm (fp32), optional
+  unsigned short* out_hi; unsigned short* out_lo; int ld_o16;  // last norm's output as 16-bit operands, optional
+  int dtype;
+};
+cudaError_t launch_norm(const NormParams& p, cudaStream_t stream);
+
+struct AttnParams {
+  const unsigned short *q_hi, *q_lo; int ldq;  // [B*Lq, ldq]; pointer already at head 0's first column
+  const unsigned short *k_hi, *k_lo; int ldk;  // [B*Lk, ldk]
+  const unsigned short *v_hi, *v_lo; int ldv;
+  const unsigned char* key_mask;               // [B, Lk] 1 = attend, or null
+  const float* rel_bias;                       // [H, 2*Lk-1] additive bias indexed by (j - i + Lk - 1), or null
+  unsigned short *o_hi, *o_lo; int ldo;        // [B*Lq, ldo]
+  int B, H, Lq, Lk, D;
+  float scale; int causal; int split; int dtype;
+};
+cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream);
+
+struct SmallAttnParams {  // tiny-sequence fp32 attention (ViT: 5 tokens, 24 heads of 32)
+  const float* qkv; int ld;        // [N*S, ld], q | k | v each W wide
+  unsigned short *o_hi, *o_lo; int ldo; float* o_f32;  // [N*S, W]
+  long long N; int S, H, W; float scale; int dtype;
+};
+cudaError_t launch_small_attention(const SmallAttnParams& p, cudaStream_t stream);
+
+struct SimtGemmGroup {  // one fp32 problem: y[M, n] = act(x[M, k] * w[n, k]^T + b)
+  const float* x; int ldx;
+  const float* w; int ldw;
+  const float* b;
+  float* y; int ldy;
+  int n, k;
+};
+cudaError_t launch_simt_gemm_grouped(const SimtGemmGroup* groups_dev, int n_groups, int M, int max_n, int act, cudaStream_t stream);
+
+// element-wise / gather kernels (misc.cu)
+cudaError_t launch_split(const float* x, long long rows, int cols, int ldx, unsigned short* hi, unsigned short* lo, int ld16,
+                         int pad_cols, float scale, int dtype, cudaStream_t s);
+cudaError_t launch_pack_weight(const float* w, int n, int k, int transposed, int ldw, unsigned short* hi, unsigned short* lo, int ld16,
+                               float scale, int dtype, cudaStream_t s);
+cudaError_t launch_assemble_history(const float* obs, const unsigned char* obs_mask, const float* act, int T, int B, int Q, int E,
+                                    int La, float* tokens, unsigned char* masks_bl, long long* pos_bl, cudaStream_t s);
+cudaError_t launch_mask_cumsum(const unsigned char* mask, int B, int L, long long* pos, cudaStream_t s);
+cudaError_t launch_add_pos_embed(const float* tok, long long stride_b, long long stride_l, const long long* ids, const float* table,
+                                 int n_pos, int B, int L, int E, float* out_f32, unsigned short* hi, unsigned short* lo, int ld16,
+                                 int dtype, int* err_flag, cudaStream_t s);
+cudaError_t launch_gather_prompt(const int* kind, const int* index, const long long* word_ids, const float* word_table,
+                                 const float* img_emb, const unsigned char* img_mask, int B, int Lp, int D, float* out,
+                                 unsigned char* mask_out, cudaStream_t s);
+cudaError_t launch_patchify(const unsigned char* img, long long N, int H, int W, int P, unsigned short* hi, unsigned short* lo, int ld16,
+                            int dtype, cudaStream_t s);
+cudaError_t launch_vit_tokens(const float* patch_out, const float* cls, const float* pos, long long N, int S, int W, float* out,
+                              cudaStream_t s);
+cudaError_t launch_bbox_norm(const long long* bbox, long long n, float* out, cudaStream_t s);
+cudaError_t launch_fill_ee(const long long* ee, const float* table, long long n_te, int Q, unsigned short* hi, unsigned short* lo,
+                           int ld16, int col0, int n_pad, int dtype, cudaStream_t s);
+cudaError_t launch_action_scale(const long long* idx, long long n, int width, const float* inv_bins, float* out, cudaStream_t s);
+cudaError_t launch_head_select(const float* logits, int B, int n_heads, const int* head_off, float* logits_norm, long long* modes,
+                               cudaStream_t s);
+cudaError_t launch_max_u8(const unsigned char* x, long long n, int* out_max, cudaStream_t s);
+
+}  // namespace vima
