@@ -72,7 +72,7 @@ def main():
         rp = ((p - p0).norm() / p0.norm()).item(); rl = ((l - l0).norm() / l0.norm()).item()
         print(f"{model} {name:11s} predicted rel-L2 {rp:.2e}  logits rel-L2 {rl:.2e}")
     O._mm = orig
-main()
+if not (len(sys.argv) > 2): main()
 
 def attention_only():
     """GEMMs exact; only QK^T / PV operands rounded (what an fp16 / bf16 tensor-core attention would do)."""
@@ -83,3 +83,44 @@ def attention_only():
         T.matmul = lambda a, b: real(a.to(dt).float(), b.to(dt).float())
         yield name
     T.matmul = real
+
+
+def ftz_study():
+    """fp16 split products when the tensor core flushes fp16 subnormal inputs, with a power-of-two activation pre-scale."""
+    import torch
+    model = "200M"
+    cfg = synth.MODEL_CFGS[model]; E = cfg["embed_dim"]; nl = cfg["xf_n_layers"]; H = cfg["sattn_n_heads"]
+    sd = {k: detgen.weight_for(k, s) for k, s in xattn_gpt_spec("xattn_gpt.", E, nl).items() if detgen.weight_for(k, s) is not None}
+    B, T, Q, Lp = 2, 8, 32, 256
+    obs = detgen.uniform("ps.obs", (T, B, Q, E)) * 1.7
+    act = detgen.uniform("ps.act", (T - 1, B, E)) * 1.7
+    pr = detgen.uniform("ps.prompt", (Lp, B, E)) * 1.7
+    om = detgen.randint("ps.om", (T, B, Q), 0, 4) > 0; om[:, :, 0] = True
+    pm = torch.ones(B, Lp, dtype=torch.bool); pm[1, 200:] = False
+    torch.set_num_threads(os.cpu_count())
+    def run():
+        with torch.no_grad():
+            return O.policy_forward(sd, obs, om, act, pr, pm, n_head=H, xattn_n_head=H)
+    p0 = run()
+    def ftz(h):  # flush fp16 subnormals
+        return torch.where(h.abs() < 6.103515625e-05, torch.zeros_like(h), h)
+    def mk(act_scale, flush):
+        def split(x, s):
+            xs = x * s
+            hi = xs.to(torch.float16).float(); lo = (xs - hi).to(torch.float16).float()
+            if flush: hi, lo = ftz(hi), ftz(lo)
+            return hi, lo
+        def mm(x, w_t):
+            ws = 2.0 ** torch.floor(torch.log2(1024.0 / w_t.abs().max()))
+            xh, xl = split(x, act_scale); wh, wl = split(w_t, ws)
+            return (xh @ wh + xl @ wh + xh @ wl) / (act_scale * ws)
+        return mm
+    orig = O._mm
+    for s, fl in [(1, False), (1, True), (16, True), (64, True), (256, True)]:
+        O._mm = mk(float(s), fl)
+        p = run()
+        print(f"fp16x3 act_scale={s:4d} ftz={fl}: predicted rel-L2 {((p - p0).norm() / p0.norm()).item():.2e}")
+    O._mm = orig
+
+if len(sys.argv) > 2 and sys.argv[2] == "ftz":
+    ftz_study()

@@ -1,0 +1,14 @@
+"""`vima.nn` surface (reference: /root/reference/vima/nn/__init__.py:1-6) on sm_100a kernels."""
+from .action import (
+    ActionDecoder,
+    ActionEmbedding,
+    Categorical,
+    CategoricalNet,
+    ContinuousActionEmbedding,
+    MultiCategorical,
+    MultiCategoricalNet,
+)
+from .basic import Conv1D, Embedding, Linear, MLPSequential, build_mlp
+from .obj_encoder import ObjEncoder, ViTEncoder, VisionTransformer
+from .t5_encoder import T5PromptEncoder, WordEmbedding
+from .xattn_gpt import XAttnGPT

@@ -1,0 +1,208 @@
+"""ObjEncoder: CLIP-style ViT over 32x32 object crops + bbox MLP -> object tokens.
+
+Module surface / state-dict keys of /root/reference/vima/nn/obj_encoder/obj_encoder.py:11-99 and
+vit/vit.py:13-46,137-236; preprocessing of vit/preprocess.py:9-43.  Kernel plan per call (both views share the ViT,
+so their crops are batched through it together):
+
+    patchify (uint8 -> normalised patch rows, fused /255, -mean, /std)  -> conv1 as tcgen05 GEMM -> +cls +pos
+    -> ln_pre [+ ln_1 chained] -> 4 x { in_proj GEMM (+bias) -> 5-token fp32 attention -> out_proj GEMM (+bias
+    +residual) -> ln_2 -> c_fc GEMM (+bias, QuickGELU) -> c_proj GEMM (+bias +residual) -> next ln_1 } -> ln_post on
+    the CLS rows -> projection GEMM;   bbox: /[256,128,128,256] -> fp32 K=4 layer -> two tcgen05 GEMMs;
+    per view Linear(1536 -> E) over the [vit | bbox] operand written in place by the two producers.
+"""
+from __future__ import annotations
+
+import math
+import os
+from collections import OrderedDict
+from typing import Dict, List
+
+import torch
+import torch.nn as nn
+
+from .. import _C
+from .. import engine as eng
+from .basic import F32GroupRunner, build_mlp, simt_linear
+
+VIMA_IMG_MEAN = (0.3471, 0.3429, 0.3383)
+VIMA_IMG_STD = (0.3011, 0.2961, 0.2956)
+
+
+class QuickGELU(nn.Module):
+    def forward(self, x):  # only a marker module: the activation runs in the c_fc GEMM epilogue
+        raise RuntimeError("QuickGELU is fused into the GEMM epilogue; call the enclosing encoder")
+
+
+class ResidualAttentionBlock(nn.Module):
+    """Parameter holder (vit.py:199-236): nn.MultiheadAttention in_proj/out_proj, ln_1, mlp.{c_fc,c_proj}, ln_2."""
+
+    def __init__(self, d_model: int, n_head: int):
+        super().__init__()
+        self.attn = nn.MultiheadAttention(d_model, n_head)
+        self.ln_1 = nn.LayerNorm(d_model)
+        self.mlp = nn.Sequential(OrderedDict([("c_fc", nn.Linear(d_model, d_model * 4)), ("gelu", QuickGELU()), ("c_proj", nn.Linear(d_model * 4, d_model))]))
+        self.ln_2 = nn.LayerNorm(d_model)
+
+
+class VisionTransformer(nn.Module):
+    def __init__(self, resolution: int, patch_size: int, width: int, layers: int, heads: int, output_dim: int):
+        super().__init__()
+        self._resolution, self._patch_size, self.output_dim = resolution, patch_size, output_dim
+        self.width, self.heads = width, heads
+        if width // heads != 32:
+            raise NotImplementedError("the fused 5-token attention kernel is built for head_dim 32 (all VIMA checkpoints)")
+        self.conv1 = nn.Conv2d(3, width, kernel_size=patch_size, stride=patch_size, bias=False)
+        scale = width ** -0.5
+        self.cls_token = nn.Parameter(scale * torch.randn(width))
+        self.pos_embed = nn.Parameter(scale * torch.randn((resolution // patch_size) ** 2 + 1, width))
+        self.ln_pre = nn.LayerNorm(width)
+        self.blocks = nn.Sequential(*[ResidualAttentionBlock(width, heads) for _ in range(layers)])
+        self.ln_post = nn.LayerNorm(width)
+        self.projection = nn.Parameter(scale * torch.randn(width, output_dim))
+        self._wc = eng.WeightCache()
+
+    def _packed(self, ctx, p):
+        def build():
+            W = {"conv": eng.pack_linear(ctx, self.conv1.weight.detach().reshape(self.width, -1), None, transposed=False, p=p),
+                 "proj": eng.pack_linear(ctx, self.projection, None, transposed=True, p=p), "blocks": []}
+            for blk in self.blocks:
+                W["blocks"].append({
+                    "in": eng.pack_linear(ctx, blk.attn.in_proj_weight, blk.attn.in_proj_bias, transposed=False, p=p),
+                    "out": eng.pack_linear(ctx, blk.attn.out_proj.weight, blk.attn.out_proj.bias, transposed=False, p=p),
+                    "fc": eng.pack_linear(ctx, blk.mlp.c_fc.weight, blk.mlp.c_fc.bias, transposed=False, p=p),
+                    "pr": eng.pack_linear(ctx, blk.mlp.c_proj.weight, blk.mlp.c_proj.bias, transposed=False, p=p),
+                })
+            return W
+
+        return self._wc.get("vit", tuple(self.parameters()), build)
+
+    def encode_u8(self, img_u8: torch.Tensor, out16: eng.Opnd = None, out16_ld: int = None):
+        """img_u8 (N,3,H,W) uint8 -> CLS features after ln_post @ projection, as 16-bit operands [N, output_dim]
+        (written into `out16`'s first columns when given)."""
+        ctx = eng.ctx_for(img_u8)
+        p = eng.prec()
+        N, C, H, Wd = img_u8.shape
+        P, Wm = self._patch_size, self.width
+        assert C == 3 and H == self._resolution and Wd == self._resolution
+        dev = img_u8.device
+        W = self._packed(ctx, p)
+        n_patch = (H // P) * (Wd // P)
+        S = n_patch + 1
+        patches = eng.Opnd(N * n_patch, 3 * P * P, dev, p.split)
+        ctx.patchify(img_u8.contiguous(), N, H, Wd, P, patches.hi, patches.lo, dtype=p.dtype)
+        pe32, _ = eng.gemm(ctx, patches, W["conv"], p, want_f32=True)
+        tok32 = torch.empty((N * S, Wm), dtype=torch.float32, device=dev)
+        ctx.vit_tokens(pe32, self.cls_token.detach(), self.pos_embed.detach(), N, S, Wm, tok32)
+        b0 = self.blocks[0]
+        x32, _, y16 = eng.norm(ctx, tok32, p, rows=N * S, cols=Wm, w=self.ln_pre.weight.detach(), b=self.ln_pre.bias.detach(), eps=self.ln_pre.eps,
+                               w2=b0.ln_1.weight.detach(), b2=b0.ln_1.bias.detach(), eps2=b0.ln_1.eps, want_f32=True, want16=True)
+        att16 = eng.Opnd(N * S, Wm, dev, p.split)
+        for i, (blk, Wb) in enumerate(zip(self.blocks, W["blocks"])):
+            qkv32, _ = eng.gemm(ctx, y16, Wb["in"], p, want_f32=True)
+            ctx.small_attention(qkv32, N=N, S=S, H=self.heads, W=Wm, scale=1.0 / math.sqrt(Wm // self.heads), o_hi=att16.hi, o_lo=att16.lo, dtype=p.dtype)
+            eng.gemm(ctx, att16, Wb["out"], p, residual=x32, out_f32=x32)
+            _, _, y16 = eng.norm(ctx, x32, p, rows=N * S, cols=Wm, w=blk.ln_2.weight.detach(), b=blk.ln_2.bias.detach(), eps=blk.ln_2.eps, want16=True)
+            _, h16 = eng.gemm(ctx, y16, Wb["fc"], p, act=_C.ACT_QUICKGELU, want16=True)
+            eng.gemm(ctx, h16, Wb["pr"], p, residual=x32, out_f32=x32)
+            if i + 1 < len(self.blocks):
+                nb = self.blocks[i + 1]
+                _, _, y16 = eng.norm(ctx, x32, p, rows=N * S, cols=Wm, w=nb.ln_1.weight.detach(), b=nb.ln_1.bias.detach(), eps=nb.ln_1.eps, want16=True)
+        # ln_post on the CLS rows (row stride S*width), then @ projection
+        _, _, cls16 = eng.norm(ctx, x32, p, rows=N, cols=Wm, ldx=S * Wm, w=self.ln_post.weight.detach(), b=self.ln_post.bias.detach(),
+                               eps=self.ln_post.eps, want16=True)
+        _, feat16 = eng.gemm(ctx, cls16, W["proj"], p, want16=out16 is None, out16=out16)
+        return feat16
+
+    def forward(self, x: torch.Tensor):
+        """x: (N,3,H,W) already-normalised float image, as the reference's VisionTransformer.forward takes it (vit.py:171)."""
+        raise NotImplementedError(
+            "vima_b200.VisionTransformer consumes uint8 crops through ViTEncoder (normalisation is fused into the patchify kernel)"
+        )
+
+
+class ViTEncoder(nn.Module):
+    def __init__(self, *, output_dim: int, resolution: int, patch_size: int, width: int, layers: int, heads: int):
+        super().__init__()
+        self.output_dim = output_dim
+        self.vit = VisionTransformer(resolution=resolution, patch_size=patch_size, width=width, layers=layers, heads=heads, output_dim=output_dim)
+        self._check_range = os.environ.get("VIMA_B200_CHECK_INPUTS", "1") != "0"
+        self._range_checked = False
+
+    def _check(self, x):
+        # preprocess.py:28 `assert img.max() > 2` is a host sync per call in the reference; here: first call only
+        if self._check_range and not self._range_checked:
+            mx = torch.zeros(1, dtype=torch.int32, device=x.device)
+            eng.ctx_for(x).max_u8(x.contiguous().view(-1), mx)
+            assert int(mx.item()) > 2, "img should be between [0, 255] before normalize"
+            self._range_checked = True
+
+    def forward(self, x: torch.Tensor):
+        """x: (..., 3, H, W) uint8 in [0,255] -> (..., output_dim) fp32 (vit.py:36-46)."""
+        assert x.dim() >= 4
+        if x.dtype != torch.uint8:
+            x = x.to(torch.uint8)
+        self._check(x)
+        lead = x.shape[:-3]
+        feat16 = self.vit.encode_u8(x.reshape(-1, *x.shape[-3:]))
+        return feat16.float(eng.prec()).view(*lead, self.output_dim)
+
+
+class ObjEncoder(nn.Module):
+    bbox_max_h = 128
+    bbox_max_w = 256
+
+    def __init__(self, *, transformer_emb_dim: int, views: List[str], vit_output_dim: int = 512, vit_resolution: int, vit_patch_size: int,
+                 vit_width: int, vit_layers: int, vit_heads: int, bbox_mlp_hidden_dim: int, bbox_mlp_hidden_depth: int):
+        super().__init__()
+        views = sorted(views)
+        self._views = views
+        self._transformer_emb_dim = transformer_emb_dim
+        self.cropped_img_encoder = ViTEncoder(output_dim=vit_output_dim, resolution=vit_resolution, patch_size=vit_patch_size, width=vit_width,
+                                              layers=vit_layers, heads=vit_heads)
+        self.bbox_mlp = nn.ModuleDict({v: build_mlp(4, hidden_dim=bbox_mlp_hidden_dim, hidden_depth=bbox_mlp_hidden_depth, output_dim=bbox_mlp_hidden_dim)
+                                       for v in views})
+        self.pre_transformer_layer = nn.ModuleDict({v: nn.Linear(self.cropped_img_encoder.output_dim + bbox_mlp_hidden_dim, transformer_emb_dim)
+                                                    for v in views})
+        self._wc = eng.WeightCache()
+
+    @property
+    def output_dim(self):
+        return self._transformer_emb_dim
+
+    def forward(self, cropped_img: Dict[str, torch.Tensor], bbox: Dict[str, torch.Tensor], mask=None):
+        """out: (..., n_objs * n_views, E) fp32  (obj_encoder.py:66-95); `mask` is unused, as in the reference."""
+        views = self._views
+        x0 = cropped_img[views[0]]
+        ctx = eng.ctx_for(x0)
+        p = eng.prec()
+        dev = x0.device
+        vit_dim = self.cropped_img_encoder.output_dim
+        imgs, counts, leads = [], [], []
+        for v in views:
+            im = cropped_img[v]
+            if im.dtype != torch.uint8:
+                im = im.to(torch.uint8)
+            leads.append(im.shape[:-3])
+            im = im.reshape(-1, *im.shape[-3:])
+            imgs.append(im)
+            counts.append(im.shape[0])
+        all_img = imgs[0] if len(imgs) == 1 else torch.cat(imgs, dim=0)
+        self.cropped_img_encoder._check(all_img)
+        n_all = all_img.shape[0]
+        bdim = self.bbox_mlp[views[0]][-1].out_features
+        cat16 = eng.Opnd(n_all, vit_dim + bdim, dev, p.split)  # [vit features | bbox features] per crop
+        self.cropped_img_encoder.vit.encode_u8(all_img, out16=cat16.sub(0, n_all, 0, vit_dim))
+        outs, r0 = [], 0
+        for v, n, lead in zip(views, counts, leads):
+            bb = bbox[v].reshape(-1, 4).to(torch.int64).contiguous()
+            bb32 = torch.empty((n, 4), dtype=torch.float32, device=dev)
+            ctx.bbox_norm(bb, n, bb32)
+            # the bbox MLP's last GEMM writes next to the ViT features of this view's rows
+            self.bbox_mlp[v](bb32, out16=cat16.sub(r0, n, vit_dim, bdim))
+            pw = self._wc.get(f"pre.{v}", (self.pre_transformer_layer[v].weight, self.pre_transformer_layer[v].bias),
+                              lambda v=v: eng.pack_linear(ctx, self.pre_transformer_layer[v].weight, self.pre_transformer_layer[v].bias, transposed=False, p=p))
+            a = cat16.sub(r0, n)
+            o32, _ = eng.gemm(ctx, a, pw, p, want_f32=True)
+            outs.append(o32.view(*lead, self._transformer_emb_dim))
+            r0 += n
+        return torch.cat(outs, dim=-2)

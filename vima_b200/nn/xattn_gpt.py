@@ -1,0 +1,249 @@
+"""XAttnGPT: cross-attention to the prompt alternating with causal self-attention over the obs/action history.
+
+Module surface and state-dict keys of /root/reference/vima/nn/seq_modeling/xattn_gpt/{xattn_gpt.py:13-177,
+components.py:14-263}; the arithmetic runs on the sm_100a kernels (tcgen05 GEMMs with fused bias / GELU / GEGLU /
+residual epilogues, fused masked attention, warp-shuffle LayerNorm).  Per layer (reference order, xattn_gpt.py:123-132):
+
+    XAttention (pre-LN, bias-free, components.py:158-228)        Block (GPT-1 post-LN, components.py:23-37)
+      q  = Wq LN(x)            k,v = Wkv (prompt + pos)             qkv = c_attn(x)
+      a  = Wo attn(q,k,v) + x                                       s   = c_proj(causal_attn(qkv)) + x
+      g  = Wg a                (gate reads UN-normalised a)         n   = LN1(s)
+      h  = gelu(W1 LN2(a)) * g                                      h   = gelu(c_fc n) * (Wg n)     [one GEMM, GLU epilogue]
+      x' = W2 h + a                                                 x'' = LN2(c_proj h + n)
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from .. import _C
+from .. import engine as eng
+from .basic import Conv1D
+
+
+class _SelfAttention(nn.Module):
+    """Parameter holder for HF openai `Attention` + the reference's persistent causal `bias` buffer (components.py:40-49)."""
+
+    def __init__(self, nx: int, n_positions: int):
+        super().__init__()
+        self.register_buffer("bias", torch.tril(torch.ones(n_positions, n_positions)).view(1, 1, n_positions, n_positions), persistent=True)
+        self.c_attn = Conv1D(3 * nx, nx)
+        self.c_proj = Conv1D(nx, nx)
+
+
+class _MLP(nn.Module):
+    def __init__(self, nx: int, geglu: bool):
+        super().__init__()
+        self.c_fc = Conv1D(4 * nx, nx)
+        self.c_proj = Conv1D(nx, 4 * nx)
+        self.gated_layer = nn.Linear(nx, 4 * nx, bias=False) if geglu else None
+
+
+class Block(nn.Module):
+    def __init__(self, nx: int, n_positions: int, n_head: int, geglu: bool, eps: float = 1e-5):
+        super().__init__()
+        self.n_head = n_head
+        self.attn = _SelfAttention(nx, n_positions)
+        self.ln_1 = nn.LayerNorm(nx, eps=eps)
+        self.mlp = _MLP(nx, geglu)
+        self.ln_2 = nn.LayerNorm(nx, eps=eps)
+
+
+class XAttention(nn.Module):
+    def __init__(self, dim: int, *, num_heads: int, ff_expanding: int, kv_n_positions: int, use_geglu: bool):
+        super().__init__()
+        if dim % num_heads != 0:
+            raise ValueError(f"dim ({dim}) must be divisible by num_heads ({num_heads}).")
+        self.num_heads = num_heads
+        self.dim = dim
+        inner = int(dim * ff_expanding)
+        self.layernorm = nn.LayerNorm(dim)
+        self.query = nn.Linear(dim, dim, bias=False)
+        self.key_value = nn.Linear(dim, 2 * dim, bias=False)
+        self.attention_out = nn.Linear(dim, dim, bias=False)
+        self.ln = nn.LayerNorm(dim)
+        self.linear1 = nn.Linear(dim, inner, bias=False)
+        self.linear2 = nn.Linear(inner, dim, bias=False)
+        self.gated_layer = nn.Linear(dim, inner, bias=False) if use_geglu else None
+        self.register_buffer("kv_position_ids", torch.arange(kv_n_positions))
+
+
+class XAttnGPT(nn.Module):
+    def __init__(
+        self,
+        embd_dim: int = 768,
+        *,
+        n_positions: int = 512,
+        n_layer: int = 12,
+        n_head: int = 12,
+        dropout: float = 0.1,
+        xattn_n_head: int = 8,
+        xattn_ff_expanding: int = 4,
+        xattn_detach_qk: bool = False,
+        xattn_n_positions: int,
+        use_geglu: bool = False,
+    ):
+        super().__init__()
+        if not use_geglu:
+            raise NotImplementedError("vima_b200.XAttnGPT implements the GEGLU configuration every VIMA checkpoint uses")
+        self.embd_dim, self.n_layer, self.n_head, self.xattn_n_head = embd_dim, n_layer, n_head, xattn_n_head
+        self.n_positions, self.xattn_n_positions = n_positions, xattn_n_positions
+        self.positions_embed = nn.Embedding(n_positions, embd_dim)
+        self.xattn_positions_embed = nn.Embedding(xattn_n_positions, embd_dim)
+        self.h = nn.ModuleList([Block(embd_dim, n_positions, n_head, use_geglu) for _ in range(n_layer)])
+        self.xattns = nn.ModuleList(
+            [XAttention(embd_dim, num_heads=xattn_n_head, ff_expanding=xattn_ff_expanding, kv_n_positions=xattn_n_positions, use_geglu=use_geglu)
+             for _ in range(n_layer)]
+        )
+        self.register_buffer("position_ids", torch.arange(n_positions))
+        self.register_buffer("xattn_position_ids", torch.arange(xattn_n_positions))
+        for m in self.modules():
+            if isinstance(m, (nn.Linear, nn.Embedding)):
+                nn.init.normal_(m.weight, std=0.02)
+        self._input_checked = False
+        self._wc = eng.WeightCache()
+
+    # ---------------------------------------------------------------------------------------------
+    def _packed(self, ctx, p):
+        def build():
+            L = []
+            for blk, xa in zip(self.h, self.xattns):
+                d = {}
+                d["wq"] = eng.pack_linear(ctx, xa.query.weight, None, transposed=False, p=p)
+                d["wkv"] = eng.pack_linear(ctx, xa.key_value.weight, None, transposed=False, p=p)
+                d["wo"] = eng.pack_linear(ctx, xa.attention_out.weight, None, transposed=False, p=p)
+                d["w1"] = eng.pack_linear(ctx, xa.linear1.weight, None, transposed=False, p=p)
+                d["wg"] = eng.pack_linear(ctx, xa.gated_layer.weight, None, transposed=False, p=p)
+                d["w2"] = eng.pack_linear(ctx, xa.linear2.weight, None, transposed=False, p=p)
+                d["c_attn"] = eng.pack_linear(ctx, blk.attn.c_attn.weight, blk.attn.c_attn.bias, transposed=True, p=p)
+                d["c_proj"] = eng.pack_linear(ctx, blk.attn.c_proj.weight, blk.attn.c_proj.bias, transposed=True, p=p)
+                d["fc_glu"] = eng.pack_glu(ctx, blk.mlp.c_fc.weight, blk.mlp.c_fc.bias, blk.mlp.gated_layer.weight,
+                                           val_transposed=True, gate_transposed=False, p=p)
+                d["mlp_proj"] = eng.pack_linear(ctx, blk.mlp.c_proj.weight, blk.mlp.c_proj.bias, transposed=True, p=p)
+                L.append(d)
+            return L
+
+        params = tuple(t for t in self.parameters())
+        return self._wc.get("layers", params, build)
+
+    def _check_input(self, obs_action_tokens, prompt_tokens, prompt_mask, batch_first, obs_action_masks):
+        """xattn_gpt.py:141-177 (first call only; host syncs)."""
+        assert obs_action_tokens.dim() == 3 and obs_action_tokens.dtype == torch.float32
+        assert prompt_tokens.dim() == 3 and prompt_tokens.dtype == torch.float32
+        if batch_first:
+            B_oa, L_oa, E_oa = obs_action_tokens.shape
+            B_p, L_p, E_p = prompt_tokens.shape
+        else:
+            L_oa, B_oa, E_oa = obs_action_tokens.shape
+            L_p, B_p, E_p = prompt_tokens.shape
+        assert B_oa == B_p and E_oa == E_p
+        if prompt_mask is not None:
+            assert prompt_mask.shape == (B_oa, L_p) or prompt_mask.shape == (B_oa, 1, L_p), \
+                f"Expect `prompt_mask` to have shape of either ({B_oa, 1, L_p}) or ({B_oa, L_p}), but got {prompt_mask.shape}"
+            assert torch.all(prompt_mask.sum(dim=-1) > 0), "each source token should attend to at least one target token"
+            assert prompt_mask.dtype == torch.bool
+        if obs_action_masks is not None:
+            assert obs_action_masks.shape == (B_oa, L_oa)
+            assert torch.all(obs_action_masks.sum(dim=-1) > 0)
+            assert obs_action_masks.dtype == torch.bool
+
+    # ---------------------------------------------------------------------------------------------
+    def forward(
+        self,
+        *,
+        obs_action_tokens: torch.Tensor,
+        obs_action_position_ids: Optional[torch.Tensor] = None,
+        prompt_tokens: torch.Tensor,
+        prompt_mask: Optional[torch.Tensor] = None,
+        prompt_position_ids: Optional[torch.Tensor] = None,
+        batch_first: bool = False,
+        obs_action_masks: Optional[torch.Tensor] = None,
+    ):
+        ctx = eng.ctx_for(obs_action_tokens)
+        p = eng.prec()
+        if not self._input_checked:
+            self._check_input(obs_action_tokens, prompt_tokens, prompt_mask, batch_first, obs_action_masks)
+        dev = obs_action_tokens.device
+        if batch_first:
+            B, L, E = obs_action_tokens.shape
+            Lp = prompt_tokens.shape[1]
+        else:
+            L, B, E = obs_action_tokens.shape
+            Lp = prompt_tokens.shape[0]
+        assert E == self.embd_dim
+        assert Lp <= self.xattn_n_positions and L <= self.n_positions
+        if obs_action_tokens.dtype != torch.float32 or prompt_tokens.dtype != torch.float32:
+            raise TypeError("XAttnGPT expects float32 tokens (xattn_gpt.py:150,152)")
+        tok = obs_action_tokens if obs_action_tokens.stride(-1) == 1 else obs_action_tokens.contiguous()
+        ptk = prompt_tokens if prompt_tokens.stride(-1) == 1 else prompt_tokens.contiguous()
+        sb, sl = (tok.stride(0), tok.stride(1)) if batch_first else (tok.stride(1), tok.stride(0))
+        psb, psl = (ptk.stride(0), ptk.stride(1)) if batch_first else (ptk.stride(1), ptk.stride(0))
+        if obs_action_position_ids is None:
+            obs_action_position_ids = self.position_ids[None, :L].expand(B, L)
+        if prompt_position_ids is None:
+            prompt_position_ids = self.xattn_position_ids[None, :Lp].expand(B, Lp)
+        oa_ids = obs_action_position_ids.to(torch.int64).contiguous()
+        pr_ids = prompt_position_ids.to(torch.int64).contiguous()
+        if prompt_mask is not None and prompt_mask.dim() == 3:
+            prompt_mask = prompt_mask.squeeze(1)
+        pmask = None if prompt_mask is None else eng.as_u8(prompt_mask)
+        omask = None if obs_action_masks is None else eng.as_u8(obs_action_masks)
+
+        M, Mp, H, Hx = B * L, B * Lp, self.n_head, self.xattn_n_head
+        d_s, d_x = E // H, E // Hx
+        err = torch.zeros(1, dtype=torch.int32, device=dev)
+        # x = tokens + positions_embed[ids] (fp32 residual stream); kv = prompt + xattn_positions_embed[ids] (operands only)
+        x32 = torch.empty((M, E), dtype=torch.float32, device=dev)
+        ctx.add_pos_embed(tok, sb, sl, oa_ids, self.positions_embed.weight.detach(), B, L, E, out_f32=x32, err_flag=err)
+        kv16 = eng.Opnd(Mp, E, dev, p.split)
+        ctx.add_pos_embed(ptk, psb, psl, pr_ids, self.xattn_positions_embed.weight.detach(), B, Lp, E, hi=kv16.hi, lo=kv16.lo,
+                          dtype=p.dtype, err_flag=err)
+        if not self._input_checked:
+            if int(err.item()) != 0:
+                raise IndexError("index out of range in self (position id outside the embedding table)")
+            self._input_checked = True
+
+        layers = self._packed(ctx, p)
+        lnw = lambda ln: (ln.weight.detach(), ln.bias.detach())
+        # first layer's query LayerNorm; later ones are chained onto the previous block's LN2
+        w, b = lnw(self.xattns[0].layernorm)
+        _, _, qin16 = eng.norm(ctx, x32, p, rows=M, cols=E, w=w, b=b, eps=self.xattns[0].layernorm.eps, want16=True)
+        for i, (blk, xa, W) in enumerate(zip(self.h, self.xattns, layers)):
+            # ---------------- XAttention ----------------
+            _, q16 = eng.gemm(ctx, qin16, W["wq"], p, want16=True)
+            _, kvp16 = eng.gemm(ctx, kv16, W["wkv"], p, want16=True)
+            c16 = eng.Opnd(M, E, dev, p.split)
+            ctx.attention(q=(q16.hi, q16.lo, q16.ld, 0), k=(kvp16.hi, kvp16.lo, kvp16.ld, 0), v=(kvp16.hi, kvp16.lo, kvp16.ld, E),
+                          o=(c16.hi, c16.lo, c16.ld, 0), B=B, H=Hx, Lq=L, Lk=Lp, D=d_x, scale=1.0 / math.sqrt(d_x), causal=False,
+                          key_mask=pmask, dtype=p.dtype)
+            a32, a16 = eng.gemm(ctx, c16, W["wo"], p, residual=x32, want_f32=True, want16=True)
+            w, b = lnw(xa.ln)
+            _, _, n16 = eng.norm(ctx, a32, p, rows=M, cols=E, w=w, b=b, eps=xa.ln.eps, want16=True)
+            g32, _ = eng.gemm(ctx, a16, W["wg"], p, want_f32=True)
+            _, h16 = eng.gemm(ctx, n16, W["w1"], p, act=_C.ACT_GELU, mul=g32, want16=True)
+            del g32
+            xb32, xb16 = eng.gemm(ctx, h16, W["w2"], p, residual=a32, want_f32=True, want16=True)
+            del h16, a32, a16
+            # ---------------- causal Block ----------------
+            _, qkv16 = eng.gemm(ctx, xb16, W["c_attn"], p, want16=True)
+            ctx.attention(q=(qkv16.hi, qkv16.lo, qkv16.ld, 0), k=(qkv16.hi, qkv16.lo, qkv16.ld, E), v=(qkv16.hi, qkv16.lo, qkv16.ld, 2 * E),
+                          o=(c16.hi, c16.lo, c16.ld, 0), B=B, H=H, Lq=L, Lk=L, D=d_s, scale=1.0 / math.sqrt(d_s), causal=True,
+                          key_mask=omask, dtype=p.dtype)
+            s32, _ = eng.gemm(ctx, c16, W["c_proj"], p, residual=xb32, want_f32=True)
+            w, b = lnw(blk.ln_1)
+            n32, _, n16 = eng.norm(ctx, s32, p, rows=M, cols=E, w=w, b=b, eps=blk.ln_1.eps, want_f32=True, want16=True)
+            _, h16 = eng.gemm(ctx, n16, W["fc_glu"], p, act=_C.ACT_GELU, want16=True)
+            s32, _ = eng.gemm(ctx, h16, W["mlp_proj"], p, residual=n32, out_f32=s32)
+            del h16
+            w, b = lnw(blk.ln_2)
+            if i + 1 < self.n_layer:
+                nxt = self.xattns[i + 1].layernorm
+                x32, _, qin16 = eng.norm(ctx, s32, p, rows=M, cols=E, w=w, b=b, eps=blk.ln_2.eps, w2=nxt.weight.detach(), b2=nxt.bias.detach(),
+                                         eps2=nxt.eps, want16=True, out_f32=x32)
+            else:
+                x32, _, _ = eng.norm(ctx, s32, p, rows=M, cols=E, w=w, b=b, eps=blk.ln_2.eps, out_f32=x32)
+        out = x32.view(B, L, E)
+        return out if batch_first else out.transpose(0, 1)
