@@ -5,7 +5,7 @@
 #include <cstring>
 
 #include "../../include/vima_b200.h"
-#include "gemm_tc.cuh"
+#include "gemm_tc_variants.cuh"
 #include "kernels.h"
 
 using namespace vima;
@@ -136,6 +136,13 @@ int vima_gemm(vima_ctx* c, const vima_gemm_desc* d, void* stream) {
   int bn = d->block_n > 0 ? d->block_n : choose_block_n(d->N, d->glu);
   if (bn > 256 || (bn % (d->glu ? 64 : 32))) return fail(c, VIMA_E_INVALID, "gemm: bad block_n %d", bn);
   if (d->glu && (d->N % bn)) return fail(c, VIMA_E_INVALID, "gemm: GLU needs N %% block_n == 0");
+  {
+    const int n_out = d->glu ? d->N / 2 : d->N;
+    const bool bad = (n_out & 3) || (d->out_f32 && ((d->ld_o32 & 3) || ((uintptr_t)d->out_f32 & 15))) ||
+                     (d->out_hi && ((d->ld_o16 & 3) || ((uintptr_t)d->out_hi & 7) || (d->out_lo && ((uintptr_t)d->out_lo & 7)))) ||
+                     (d->mul && ((d->ld_mul & 3) || ((uintptr_t)d->mul & 15))) || (d->residual && ((d->ld_res & 3) || ((uintptr_t)d->residual & 15)));
+    if (bad) return fail(c, VIMA_E_INVALID, "gemm: epilogue tensors need N %% 4 == 0, ld %% 4 == 0 and 16-byte (fp32) / 8-byte (16-bit) aligned bases");
+  }
 
   GemmParams p;
   memset(&p, 0, sizeof(p));
@@ -167,15 +174,13 @@ int vima_gemm(vima_ctx* c, const vima_gemm_desc* d, void* stream) {
   if (n_stages < 2) return fail(c, VIMA_E_UNSUPPORTED, "gemm: not enough shared memory for 2 stages");
   p.n_stages = n_stages;
   const size_t smem = gemm_smem_bytes(bn, split, n_stages);
-  if (!c->gemm_attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin);
-    if (e != cudaSuccess) return cuda_fail(c, e, "cudaFuncSetAttribute(gemm)");
-    c->gemm_attr_set = true;
-  }
   const int tiles = ((d->M + GEMM_BM - 1) / GEMM_BM) * ((d->N + bn - 1) / bn);
   const int grid = tiles < c->sm_count ? tiles : c->sm_count;
-  gemm_tc_kernel<<<grid, GEMM_THREADS, smem, (cudaStream_t)stream>>>(p);
-  LAUNCHED(c, cudaGetLastError(), "gemm_tc_kernel");
+  GemmLaunch l;
+  l.act = d->act; l.glu = d->glu != 0; l.mul = d->mul != nullptr; l.res = d->residual != nullptr;
+  l.o32 = d->out_f32 != nullptr; l.o16 = d->out_hi != nullptr; l.dtype = d->dtype;
+  if (d->dtype == DT_BF16) { LAUNCHED(c, launch_gemm_tc_bf16(p, l, grid, smem, c->max_smem_optin, (cudaStream_t)stream), "gemm_tc_kernel"); }
+  LAUNCHED(c, launch_gemm_tc_f16(p, l, grid, smem, c->max_smem_optin, (cudaStream_t)stream), "gemm_tc_kernel");
 }
 
 int vima_gemm_f32_grouped(vima_ctx* c, const vima_f32_gemm_group* groups_dev, int n_groups, int M, int max_n, int act, void* stream) {

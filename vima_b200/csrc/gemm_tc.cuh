@@ -4,11 +4,14 @@
 //    pairs: in split mode the kernel accumulates A_hi*B_hi + A_lo*B_hi + A_hi*B_lo in the SAME fp32 TMEM
 //    accumulator, which restores ~fp32 products (see DESIGN.md "operand precision").
 //  * Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
-//    warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM -> registers -> smem transpose -> coalesced global).
+//    warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM -> registers -> smem transpose -> 128-bit coalesced global).
 //  * smem ring of `n_stages` stages {A_hi,[A_lo],B_hi,[B_lo]} in the 128-byte swizzled K-major layout that TMA
 //    writes and the UMMA descriptors read; two 256-column fp32 accumulators in TMEM so the epilogue of tile i
 //    overlaps the main loop of tile i+1.
 //  * Epilogue: acc*scale + bias -> activation -> (GLU pair product) -> *mul -> +residual -> fp32 and/or (hi,lo).
+//    The epilogue is specialised at compile time (EpiCfg) for the combinations the VIMA path uses; a generic
+//    runtime-flag variant covers everything else.  v0 of this kernel was epilogue-bound by 10x (scalar 2-byte
+//    stores, runtime flag tests per element: profiles/r1_gemm_v0_epilogue_bound.csv).
 #pragma once
 #include "common.cuh"
 
@@ -19,7 +22,8 @@ constexpr int GEMM_BK = 64;                       // 64 x 2 B = 128 B = one swiz
 constexpr int GEMM_A_TILE_BYTES = GEMM_BM * 128;  // 16 KB
 constexpr int GEMM_THREADS = 256;
 constexpr int GEMM_MAX_STAGES = 8;
-constexpr int GEMM_STAGING_BYTES = 4 * 32 * 33 * 4;  // per-epilogue-warp 32x33 fp32 transpose buffers
+constexpr int GEMM_ST_LD = 36;                               // padded row of the transpose buffer (floats)
+constexpr int GEMM_STAGING_BYTES = 4 * 32 * GEMM_ST_LD * 4;  // per-epilogue-warp 32x36 fp32 transpose buffers
 constexpr int GEMM_TMEM_COLS = 512;
 
 struct alignas(64) GemmParams {
@@ -44,12 +48,122 @@ struct alignas(64) GemmParams {
   int ld_o16;
 };
 
+// Compile-time epilogue description. GENERIC: every flag is read from GemmParams at run time instead.
+template <bool GENERIC_, int ACT_, bool GLU_, bool MUL_, bool RES_, bool O32_, bool O16_, int DT_>
+struct EpiCfg {
+  static constexpr bool GENERIC = GENERIC_;
+  static constexpr int ACT = ACT_;
+  static constexpr bool GLU = GLU_, MUL = MUL_, RES = RES_, O32 = O32_, O16 = O16_;
+  static constexpr int DT = DT_;
+};
+
 __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
   // start address [0,14) (>>4) | LBO [16,30) (ignored for swizzled K-major; 1) | SBO [32,46) = 8 rows * 128 B
   // | version [46,48) = 1 (sm_100) | layout type [61,64) = 2 (SWIZZLE_128B)
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
+template <int ACT>
+__device__ __forceinline__ float act_ct(float x) {
+  if constexpr (ACT == ACT_RELU) return fmaxf(x, 0.f);
+  else if constexpr (ACT == ACT_QUICKGELU) return quick_gelu(x);
+  else if constexpr (ACT == ACT_GELU) return gelu_erf(x);
+  else return x;
+}
+
+template <int DT>
+__device__ __forceinline__ void split4(const float4& y, uint2& hi, uint2& lo) {
+  unsigned short h0, h1, h2, h3, l0, l1, l2, l3;
+  split16<DT>(y.x, h0, l0); split16<DT>(y.y, h1, l1); split16<DT>(y.z, h2, l2); split16<DT>(y.w, h3, l3);
+  hi = make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
+  lo = make_uint2((uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2 | ((uint32_t)l3 << 16));
+}
+
+// One accumulator tile (this warp's 32 rows): TMEM -> registers (row per thread) -> bias/act/GLU -> smem transpose
+// -> [rows of 4 x 8 lanes x float4] -> mul / residual / stores, all 128-bit and coalesced.
+template <class E>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_row, const float* __restrict__ sb, float* __restrict__ st,
+                                              int lane, int row_base, int tn, int bn_out, int n_out) {
+  const bool glu = E::GENERIC ? (p.glu != 0) : E::GLU;
+  const bool has_mul = E::GENERIC ? (p.mul != nullptr) : E::MUL;
+  const bool has_res = E::GENERIC ? (p.residual != nullptr) : E::RES;
+  const bool o32 = E::GENERIC ? (p.out_f32 != nullptr) : E::O32;
+  const bool o16 = E::GENERIC ? (p.out_hi != nullptr) : E::O16;
+  const float scale = p.acc_scale;
+  const int sub = lane >> 3;        // row within a group of 4
+  const int c4 = (lane & 7) * 4;    // first of this lane's 4 columns inside the 32-column chunk
+  for (int j = 0; j < bn_out; j += 32) {
+    uint32_t v[32];
+    tmem_ld_32x32(t_row + j, v);
+    float x[32];
+    if (glu) {
+      uint32_t g[32];
+      tmem_ld_32x32(t_row + bn_out + j, g);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 b1 = *reinterpret_cast<const float4*>(sb + j + i);
+        const float4 b2 = *reinterpret_cast<const float4*>(sb + bn_out + j + i);
+        const float bb1[4] = {b1.x, b1.y, b1.z, b1.w}, bb2[4] = {b2.x, b2.y, b2.z, b2.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float a = __uint_as_float(v[i + q]) * scale + bb1[q];
+          a = E::GENERIC ? apply_act(p.act, a) : act_ct<E::ACT>(a);
+          x[i + q] = a * (__uint_as_float(g[i + q]) * scale + bb2[q]);
+        }
+      }
+    } else {
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 b1 = *reinterpret_cast<const float4*>(sb + j + i);
+        const float bb1[4] = {b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float a = __uint_as_float(v[i + q]) * scale + bb1[q];
+          x[i + q] = E::GENERIC ? apply_act(p.act, a) : act_ct<E::ACT>(a);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(st + lane * GEMM_ST_LD + i) = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
+    __syncwarp();
+    const int col = tn * bn_out + j + c4;
+    const bool col_ok = col < n_out;  // n_out % 4 == 0 (checked on the host)
+    float4 y[8], mm[8], rr[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {  // issue every global load of the chunk before the first use
+      const int row = row_base + it * 4 + sub;
+      const bool ok = col_ok && row < p.M;
+      if (has_mul) mm[it] = ok ? __ldg(reinterpret_cast<const float4*>(p.mul + (size_t)row * p.ld_mul + col)) : make_float4(1.f, 1.f, 1.f, 1.f);
+      if (has_res) rr[it] = ok ? __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)row * p.ld_res + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) y[it] = *reinterpret_cast<const float4*>(st + (it * 4 + sub) * GEMM_ST_LD + c4);
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = row_base + it * 4 + sub;
+      if (!(col_ok && row < p.M)) continue;
+      float4 o = y[it];
+      if (has_mul) { o.x *= mm[it].x; o.y *= mm[it].y; o.z *= mm[it].z; o.w *= mm[it].w; }
+      if (has_res) { o.x += rr[it].x; o.y += rr[it].y; o.z += rr[it].z; o.w += rr[it].w; }
+      if (o32) *reinterpret_cast<float4*>(p.out_f32 + (size_t)row * p.ld_o32 + col) = o;
+      if (o16) {
+        uint2 hi, lo;
+        if (E::GENERIC) {
+          if (p.dtype == DT_F16) split4<DT_F16>(o, hi, lo); else split4<DT_BF16>(o, hi, lo);
+        } else {
+          split4<E::DT>(o, hi, lo);
+        }
+        *reinterpret_cast<uint2*>(p.out_hi + (size_t)row * p.ld_o16 + col) = hi;
+        if (p.out_lo) *reinterpret_cast<uint2*>(p.out_lo + (size_t)row * p.ld_o16 + col) = lo;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <class E>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages][staging][bias 2x256 f32][barriers][tmem ptr]
@@ -167,10 +281,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int we = warp - 4;  // == warp % 4 : TMEM lane quadrant
-    float* st = staging + we * (32 * 33);
+    float* st = staging + we * (32 * GEMM_ST_LD);
     const int et = threadIdx.x - 128;  // 0..127
-    const int n_out = p.glu ? p.N / 2 : p.N;
-    const int bn_out = p.glu ? BN / 2 : BN;
+    const bool glu = E::GENERIC ? (p.glu != 0) : E::GLU;
+    const int n_out = glu ? p.N / 2 : p.N;
+    const int bn_out = glu ? BN / 2 : BN;
     int ab = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -184,49 +299,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       mbar_wait(&tmem_full[ab], aphase);
       tcgen05_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(we * 32) << 16) + (uint32_t)(ab * 256);
-      const int row_base = m0 + we * 32;
-      for (int j = 0; j < bn_out; j += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_row + j, v);
-        float x[32];
-        if (p.glu) {
-          uint32_t g[32];
-          tmem_ld_32x32(t_row + bn_out + j, g);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float a = apply_act(p.act, __uint_as_float(v[i]) * p.acc_scale + sb[j + i]);
-            x[i] = a * (__uint_as_float(g[i]) * p.acc_scale + sb[bn_out + j + i]);
-          }
-        } else {
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) x[i] = apply_act(p.act, __uint_as_float(v[i]) * p.acc_scale + sb[j + i]);
-        }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) st[lane * 33 + i] = x[i];
-        __syncwarp();
-        const int col = tn * bn_out + j + lane;
-        const bool col_ok = col < n_out;
-        const int rmax = min(32, p.M - row_base);
-#pragma unroll 4
-        for (int r = 0; r < rmax; ++r) {
-          float y = st[r * 33 + lane];
-          const size_t row = (size_t)(row_base + r);
-          if (col_ok) {
-            if (p.mul) y *= __ldg(p.mul + row * p.ld_mul + col);
-            if (p.residual) y += __ldg(p.residual + row * p.ld_res + col);
-            if (p.out_f32) p.out_f32[row * p.ld_o32 + col] = y;
-            if (p.out_hi) {
-              unsigned short hi, lo;
-              split16_rt(p.dtype, y, hi, lo);
-              p.out_hi[row * p.ld_o16 + col] = hi;
-              if (p.out_lo) p.out_lo[row * p.ld_o16 + col] = lo;
-            }
-          }
-        }
-        __syncwarp();
-      }
+      epilogue_tile<E>(p, t_row, sb, st, lane, m0 + we * 32, tn, bn_out, n_out);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[ab]);
