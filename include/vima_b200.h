@@ -156,10 +156,15 @@ int vima_add_pos_embed(vima_ctx*, const float* tok, int64_t stride_b, int64_t st
 int vima_gather_prompt(vima_ctx*, const int32_t* kind, const int32_t* index, const int64_t* word_ids, const float* word_table,
                        const float* img_emb, const uint8_t* img_mask, int B, int Lp, int D, float* out, uint8_t* mask_out, void* stream);
 
+/* vima_gato_policy.py:150-182 (decoder-only baseline): mask [B,L] = [prompt_mask | ones]; position ids: arange over the n
+ * valid prompt tokens, n-1 on padded prompt slots, then n, n+1, ... */
+int vima_gato_positions(vima_ctx*, const uint8_t* prompt_mask, int B, int Lp, int L, uint8_t* mask_out, int64_t* pos_out, void* stream);
+
 /* ---- object-encoder front end ---------------------------------------------------------------------------------
  * preprocess.py:23-43 + vit.py:151-157,172: uint8 crops (N,3,H,W) -> normalised patch rows (hi, lo) [N*(H/P)*(W/P), ld16]. */
 int vima_patchify(vima_ctx*, const uint8_t* img, int64_t N, int H, int W, int P, void* hi, void* lo, int ld16, int dtype, void* stream);
-/* vit.py:173-179: tokens[n,0] = cls + pos[0]; tokens[n,1+p] = patch_out[n*(S-1)+p] + pos[1+p]. */
+/* vit.py:173-179: tokens[n,0] = cls + pos[0]; tokens[n,1+p] = patch_out[n*(S-1)+p] + pos[1+p].
+ * cls == NULL (Gato ViT, vit.py:123-126): tokens[n,s] = patch_out[n*S+s] + pos[s]. */
 int vima_vit_tokens(vima_ctx*, const float* patch_out, const float* cls, const float* pos, int64_t N, int S, int W, float* out, void* stream);
 /* obj_encoder.py:79-85 */
 int vima_bbox_norm(vima_ctx*, const int64_t* bbox, int64_t n, float* out, void* stream);

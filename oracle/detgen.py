@@ -68,11 +68,13 @@ def weight_for(key: str, shape, seed: int = 0) -> torch.Tensor | None:
     if nd == 1:
         if key.endswith(".weight"):  # norm gains
             return 1.0 + 0.1 * uniform(key, shape, seed)
-        if key.endswith("cls_token"):
+        if key.endswith("cls_token") or key.endswith("prompt_sep_token"):
             return 0.5 * uniform(key, shape, seed)
         return 0.1 * uniform(key, shape, seed)  # biases
     if "relative_attention_bias" in key:
         return 0.5 * uniform(key, shape, seed)
+    if key.endswith("tokens_embed.weight"):
+        return 0.02 * uniform(key, shape, seed)
     if "positions_embed" in key or key.endswith("pos_embed"):
         return 0.1 * uniform(key, shape, seed)
     if "end_effector_encoder" in key:

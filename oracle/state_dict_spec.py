@@ -137,3 +137,52 @@ def state_dict_spec(*, embed_dim: int, xf_n_layers: int, sattn_n_heads: int = 0,
         sd["t5_prompt_encoder_post_layer.weight"] = (E, 768)
     sd.update(mlp_spec("prompt_obj_post_layer.", [E, 768, 768, 768]))
     return sd
+
+
+def gato_state_dict_spec(*, embed_dim: int, n_layer: int, n_head: int = 0, vocab_size: int = 40478, n_positions: int = 512):
+    """`VIMAGatoPolicy.state_dict()` of the reference under the transformers version in this image (no `attn.bias`)."""
+    E = embed_dim
+    sd = OrderedDict()
+    sd["prompt_sep_token"] = (E,)
+    sd["transformer.lm.position_ids"] = (n_positions,)
+    sd["transformer.lm.tokens_embed.weight"] = (vocab_size, E)
+    sd["transformer.lm.positions_embed.weight"] = (n_positions, E)
+    for i in range(n_layer):
+        h = f"transformer.lm.h.{i}."
+        sd[h + "attn.c_attn.weight"] = (E, 3 * E)
+        sd[h + "attn.c_attn.bias"] = (3 * E,)
+        sd[h + "attn.c_proj.weight"] = (E, E)
+        sd[h + "attn.c_proj.bias"] = (E,)
+        sd[h + "ln_1.weight"] = (E,)
+        sd[h + "ln_1.bias"] = (E,)
+        sd[h + "mlp.c_fc.weight"] = (E, 4 * E)
+        sd[h + "mlp.c_fc.bias"] = (4 * E,)
+        sd[h + "mlp.c_proj.weight"] = (4 * E, E)
+        sd[h + "mlp.c_proj.bias"] = (E,)
+        sd[h + "mlp.gated_layer.weight"] = (4 * E, E)
+        sd[h + "ln_2.weight"] = (E,)
+        sd[h + "ln_2.bias"] = (E,)
+    v = "obj_encoder.cropped_img_encoder.vit."
+    full = vit_spec(v, width=768, layers=4, res=32, patch=16, out=E)
+    sd[v + "pos_embed"] = (8, 768)
+    sd[v + "projection"] = (768, E)
+    sd[v + "conv1.weight"] = (768, 3, 32, 32)
+    for k, shp in full.items():
+        if k.split(".")[-2] in ("ln_pre",) or ".blocks." in k or ".ln_post." in k:
+            sd[k] = shp
+    sd["end_effector_encoder.weight"] = (2, 2)
+    sd["obs_fusion_layer.weight"] = (E, E + 2)
+    sd["obs_fusion_layer.bias"] = (E,)
+    for k, n_in in ACTION_IN.items():
+        sd.update(mlp_spec(f"action_encoder._embed_dict.{k}._layer.", [n_in, 256, 256]))
+    sd["action_encoder._post_layer.weight"] = (E, 1024)
+    sd["action_encoder._post_layer.bias"] = (E,)
+    for k, dims in ACTION_DIMS.items():
+        for j, n in enumerate(dims):
+            sd.update(mlp_spec(f"action_decoder._decoders.{k}.mlps.{j}.", [E, 512, 512, n]))
+    sd["prompt_embedding._embed_layer.weight"] = (32128, 768)
+    sd.update(t5_spec("t5_prompt_encoder.t5."))
+    if E != 768:
+        sd["t5_prompt_encoder_post_layer.weight"] = (E, 768)
+    sd.update(mlp_spec("prompt_obj_post_layer.", [E, 768, 768, 768]))
+    return sd

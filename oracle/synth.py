@@ -133,3 +133,43 @@ def make_actions(case: Case, T: int):
         cols = [detgen.randint(f"{case.name}.act.{k}.{j}", (max(T - 1, 0), case.B, 1), 0, n, case.seed) for j, n in enumerate(dims)]
         out[k] = torch.cat(cols, dim=-1)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# VIMA-Gato baseline inputs: whole 64x128 RGB views instead of object crops
+# ------------------------------------------------------------------------------------------------
+GATO_CFGS = {"gato_tiny": dict(embed_dim=256, n_layer=2, n_head=8), "gato_200M": dict(embed_dim=768, n_layer=22, n_head=24)}
+GATO_CASES = {
+    "gato_small": Case("gato_small", "gato_tiny", B=2, T=2, n_slots=8, n_words=6, n_imgs=1, ragged=True, seed=21),
+    "gato_cfg5": Case("gato_cfg5", "gato_200M", B=256, T=8, n_slots=8, n_words=240, n_imgs=1, seed=22),
+}
+
+
+def _rgb(tag: str, lead: tuple, seed: int):
+    out = {}
+    for v in VIEWS:
+        img = detgen.randint(f"{tag}.rgb.{v}", lead + (3, 64, 128), 0, 256, seed).to(torch.uint8)
+        img.view(-1)[0] = 200
+        out[v] = img
+    return out
+
+
+def make_gato_prompt(case: Case):
+    token_types, n_words_total, n_imgs_total = [], 0, 0
+    for b in range(case.B):
+        nw = case.n_words
+        if case.ragged and b > 0:
+            nw = int(detgen.randint(f"{case.name}.nw.{b}", (1,), max(1, case.n_words // 2), case.n_words + 1, case.seed))
+        tt = [0] * nw
+        for j in range(case.n_imgs):
+            tt.insert(min(len(tt), 2 + j), 1)
+        token_types.append(tt)
+        n_words_total += nw
+        n_imgs_total += case.n_imgs
+    word_batch = detgen.randint(f"{case.name}.words", (n_words_total,), 0, 32100, case.seed)
+    return token_types, word_batch, {"rgb": _rgb(f"{case.name}.prompt", (n_imgs_total,), case.seed)}
+
+
+def make_gato_obs(case: Case, T: Optional[int] = None, tag: str = "obs"):
+    T = case.T if T is None else T
+    return {"ee": detgen.randint(f"{case.name}.{tag}.ee", (T, case.B), 0, 2, case.seed), "rgb": _rgb(f"{case.name}.{tag}", (T, case.B), case.seed)}

@@ -428,3 +428,106 @@ def policy_step(sd: SD, *, obs, history_obs_tokens, history_obs_masks, history_a
     modes = action_modes(logits)
     act_tok = forward_action_token(sd, modes)
     return dict(obs_tokens=obs_tok, obs_masks=obs_msk, predicted=pred, logits=logits, actions=modes, action_token=act_tok)
+
+
+# ------------------------------------------------------------------------------------------------
+# VIMA-Gato baseline (decoder-only; BASELINE.json configs[4])
+# ------------------------------------------------------------------------------------------------
+def gato_vit_forward(sd: SD, p: str, img: torch.Tensor, heads: int = 24, patch: int = 32) -> torch.Tensor:
+    """GatoVisionTransformerRectangular.forward, vima/nn/obj_encoder/vit/vit.py:120-134 (no CLS; every patch token kept)."""
+    N = img.shape[0]
+    w = sd[p + "conv1.weight"]
+    width = w.shape[0]
+    patches = F.unfold(img, kernel_size=patch, stride=patch).transpose(1, 2)
+    x = _mm(patches, w.reshape(width, -1).t()) + sd[p + "pos_embed"]
+    x = layer_norm(x, sd[p + "ln_pre.weight"], sd[p + "ln_pre.bias"])
+    S = x.shape[1]
+    d = width // heads
+    i = 0
+    while f"{p}blocks.{i}.ln_1.weight" in sd:
+        b = f"{p}blocks.{i}."
+        y = layer_norm(x, sd[b + "ln_1.weight"], sd[b + "ln_1.bias"])
+        q, k, v = linear(y, sd[b + "attn.in_proj_weight"], sd[b + "attn.in_proj_bias"]).split(width, dim=-1)
+        q = q.view(N, S, heads, d).transpose(1, 2)
+        k = k.view(N, S, heads, d).transpose(1, 2)
+        v = v.view(N, S, heads, d).transpose(1, 2)
+        att = torch.softmax(torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(d), dim=-1)
+        o = torch.matmul(att, v).transpose(1, 2).reshape(N, S, width)
+        x = x + linear(o, sd[b + "attn.out_proj.weight"], sd[b + "attn.out_proj.bias"])
+        y = layer_norm(x, sd[b + "ln_2.weight"], sd[b + "ln_2.bias"])
+        h = linear(y, sd[b + "mlp.c_fc.weight"], sd[b + "mlp.c_fc.bias"])
+        h = h * torch.sigmoid(1.702 * h)
+        x = x + linear(h, sd[b + "mlp.c_proj.weight"], sd[b + "mlp.c_proj.bias"])
+        i += 1
+    x = layer_norm(x, sd[p + "ln_post.weight"], sd[p + "ln_post.bias"])
+    return _mm(x, sd[p + "projection"])
+
+
+def gato_obj_encoder(sd: SD, p: str, rgb: dict) -> torch.Tensor:
+    """GatoMultiViewRGBEncoder.forward, vima/nn/obj_encoder/obj_encoder.py:127-142."""
+    outs = []
+    for view in VIEWS:
+        img = rgb[view]
+        lead = img.shape[:-3]
+        f = gato_vit_forward(sd, p + "cropped_img_encoder.vit.", image_preprocess(img).flatten(0, img.dim() - 4))
+        outs.append(f.view(*lead, *f.shape[-2:]))
+    return torch.cat(outs, dim=-2)
+
+
+def hfgpt_forward(sd: SD, p: str, x: torch.Tensor, mask: torch.Tensor, position_ids: torch.Tensor, n_head: int) -> torch.Tensor:
+    """HFGPT.forward -> OpenAIGPTModel.forward, vima/nn/seq_modeling/gpt/gpt.py:46-221. x (L,B,E), mask (B,L), ids (B,L)."""
+    h = x.transpose(0, 1) + sd[p + "lm.positions_embed.weight"][position_ids]
+    add_mask = (1.0 - mask[:, None, None, :].to(torch.float32)) * FP32_MIN
+    i = 0
+    while f"{p}lm.h.{i}.ln_1.weight" in sd:
+        h = gpt_block(sd, f"{p}lm.h.{i}.", h, add_mask, n_head)
+        i += 1
+    return h.transpose(0, 1)
+
+
+def gato_forward_prompt_assembly(sd: SD, prompts):
+    """VIMAGatoPolicy.forward_prompt_assembly, vima/policy/vima_gato_policy.py:193-251."""
+    token_types, word_batch, image_batch = prompts
+    word_emb = sd["prompt_embedding._embed_layer.weight"][word_batch]
+    img_emb = mlp_seq(sd, "prompt_obj_post_layer.", gato_obj_encoder(sd, "obj_encoder.", image_batch["rgb"]), (0, 3, 6))
+    nq = img_emb.shape[-2]
+    lens = [sum(1 if t == 0 else nq for t in tt) for tt in token_types]
+    B, L_max = len(token_types), max(lens)
+    toks = torch.zeros(B, L_max, img_emb.shape[-1])
+    masks = torch.zeros(B, L_max, dtype=torch.bool)
+    wp = ip = 0
+    for b, tt in enumerate(token_types):
+        pos = 0
+        for t in tt:
+            if t == 0:
+                toks[b, pos] = word_emb[wp]; wp += 1; pos += 1
+            else:
+                toks[b, pos:pos + nq] = img_emb[ip]; ip += 1; pos += nq
+        masks[b, :pos] = True
+    enc = t5_encoder_forward(sd, "t5_prompt_encoder.t5.encoder.", toks, masks)
+    if "t5_prompt_encoder_post_layer.weight" in sd:
+        enc = linear(enc, sd["t5_prompt_encoder_post_layer.weight"])
+    return enc.transpose(0, 1), masks
+
+
+def gato_forward_obs_token(sd: SD, obs):
+    """VIMAGatoPolicy.forward_obs_token, vima_gato_policy.py:253-262."""
+    img_feats = gato_obj_encoder(sd, "obj_encoder.", obs["rgb"])
+    ee_feats = sd["end_effector_encoder.weight"][obs["ee"]].unsqueeze(2).repeat(1, 1, img_feats.shape[-2], 1)
+    return linear(torch.cat([img_feats, ee_feats], dim=-1), sd["obs_fusion_layer.weight"], sd["obs_fusion_layer.bias"])
+
+
+def gato_policy_forward(sd: SD, obs_token, action_token, prompt_token, prompt_token_mask, *, n_head: int):
+    """VIMAGatoPolicy.forward, vima_gato_policy.py:120-191."""
+    T, B, Q, E = obs_token.shape
+    Lp = prompt_token.shape[0]
+    hist, _, _ = assemble_history(obs_token, torch.ones(T, B, Q, dtype=torch.bool), action_token)
+    tokens = torch.cat([prompt_token, sd["prompt_sep_token"].expand(1, B, E), hist], dim=0)
+    L = tokens.shape[0]
+    mask = torch.cat([prompt_token_mask, torch.ones(B, L - Lp, dtype=torch.bool)], dim=1)
+    n_valid = prompt_token_mask.sum(dim=1)
+    ids = []
+    for n in n_valid.tolist():
+        ids.append(torch.cat([torch.arange(n), torch.full((Lp - n,), n - 1), torch.arange(n, n + L - Lp)]))
+    out = hfgpt_forward(sd, "transformer.", tokens, mask, torch.stack(ids).long(), n_head)
+    return out[Lp + 1 + Q - 1 :: Q + 1]

@@ -100,8 +100,39 @@ def run_case(ref_vima, case_name: str):
     return out
 
 
+def run_gato_case(ref_vima, case_name: str):
+    import torch
+
+    from oracle import detgen, synth
+
+    case = synth.GATO_CASES[case_name]
+    policy = ref_vima.VIMAGatoPolicy(**synth.GATO_CFGS[case.model]).eval()
+    detgen.fill_module_(policy)
+    DataDict = sys.modules["vima.utils"].DataDict
+    out = {}
+    with torch.no_grad():
+        token_types, word_batch, image_batch = synth.make_gato_prompt(case)
+        prompt_tokens, prompt_masks = policy.forward_prompt_assembly((token_types, word_batch, DataDict(image_batch)))
+        pack(out, "prompt_tokens", prompt_tokens)
+        pack(out, "prompt_masks", prompt_masks)
+        obs = synth.make_gato_obs(case)
+        obs_tokens = policy.forward_obs_token(DataDict({"ee": obs["ee"], "rgb": DataDict(obs["rgb"])}))
+        pack(out, "obs_tokens", obs_tokens)
+        action_tokens = policy.forward_action_token(synth.make_actions(case, case.T)) if case.T > 1 else None
+        if action_tokens is not None:
+            pack(out, "action_tokens", action_tokens)
+        predicted = policy.forward(obs_token=obs_tokens, action_token=action_tokens, prompt_token=prompt_tokens, prompt_token_mask=prompt_masks)
+        pack(out, "predicted", predicted)
+        dists = policy.forward_action_decoder(predicted[-1:])
+        raw_logits = torch.cat([mlp(predicted[-1:]) for k in policy.action_decoder._decoders for mlp in policy.action_decoder._decoders[k].mlps], dim=-1)
+        pack(out, "logits_raw", raw_logits)
+        for k, v in dists.items():
+            pack(out, f"mode.{k}", v.mode())
+    return out
+
+
 def main():
-    names = sys.argv[1:] or CPU_CASES
+    names = sys.argv[1:] or (CPU_CASES + ["gato_small"])
     from oracle.ref_shim import load_reference
 
     ref_vima = load_reference()
@@ -110,7 +141,7 @@ def main():
     torch.set_num_threads(os.cpu_count())
     for n in names:
         t0 = time.time()
-        out = run_case(ref_vima, n)
+        out = run_gato_case(ref_vima, n) if n.startswith("gato") else run_case(ref_vima, n)
         path = os.path.join(HERE, f"{n}.npz")
         np.savez_compressed(path, **out)
         print(f"{n}: {len(out)} arrays -> {path} ({os.path.getsize(path)/1e3:.0f} kB) in {time.time()-t0:.1f}s")

@@ -77,7 +77,7 @@ EXPORTS = [
     "vima_split_f32", "vima_pack_weight", "vima_gemm", "vima_glu_block_n", "vima_gemm_f32_grouped", "vima_norm",
     "vima_attention", "vima_small_attention", "vima_assemble_history", "vima_mask_cumsum", "vima_add_pos_embed",
     "vima_gather_prompt", "vima_patchify", "vima_vit_tokens", "vima_bbox_norm", "vima_fill_ee", "vima_max_u8",
-    "vima_action_scale", "vima_head_select",
+    "vima_action_scale", "vima_head_select", "vima_gato_positions",
 ]
 
 
@@ -250,8 +250,13 @@ class Context:
         self._ck(self.lib.vima_patchify(self.h, c_void_p(img_u8.data_ptr()), c_i64(N), H, W, P, c_void_p(hi.data_ptr()), c_void_p(_ptr(lo)),
                                         hi.stride(0), dtype, c_void_p(_stream())), "patchify")
 
+    def gato_positions(self, prompt_mask_u8, L, mask_out, pos_out):
+        B, Lp = prompt_mask_u8.shape
+        self._ck(self.lib.vima_gato_positions(self.h, c_void_p(prompt_mask_u8.data_ptr()), B, Lp, L, c_void_p(mask_out.data_ptr()),
+                                              c_void_p(pos_out.data_ptr()), c_void_p(_stream())), "gato_positions")
+
     def vit_tokens(self, patch_out, cls, pos, N, S, W, out):
-        self._ck(self.lib.vima_vit_tokens(self.h, c_void_p(patch_out.data_ptr()), c_void_p(cls.data_ptr()), c_void_p(pos.data_ptr()), c_i64(N),
+        self._ck(self.lib.vima_vit_tokens(self.h, c_void_p(patch_out.data_ptr()), c_void_p(_ptr(cls)), c_void_p(pos.data_ptr()), c_i64(N),
                                           S, W, c_void_p(out.data_ptr()), c_void_p(_stream())), "vit_tokens")
 
     def bbox_norm(self, bbox_i64, n, out):

@@ -299,6 +299,12 @@ int vima_fill_ee(vima_ctx* c, const int64_t* ee, const float* table, int64_t n_t
            "fill_ee");
 }
 
+int vima_gato_positions(vima_ctx* c, const uint8_t* prompt_mask, int B, int Lp, int L, uint8_t* mask_out, int64_t* pos_out, void* stream) {
+  CHECK_CTX(c);
+  if (!prompt_mask || !mask_out || !pos_out || L < Lp) return fail(c, VIMA_E_INVALID, "gato_positions: bad arguments");
+  LAUNCHED(c, launch_gato_positions(prompt_mask, B, Lp, L, mask_out, (long long*)pos_out, (cudaStream_t)stream), "gato_positions");
+}
+
 int vima_max_u8(vima_ctx* c, const uint8_t* x, int64_t n, int* out_max, void* stream) {
   CHECK_CTX(c);
   LAUNCHED(c, launch_max_u8(x, n, out_max, (cudaStream_t)stream), "max_u8");

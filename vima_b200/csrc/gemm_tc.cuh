@@ -288,7 +288,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     const int bn_out = glu ? BN / 2 : BN;
     int ab = 0;
     uint32_t aphase = 0;
+    const bool has_mul = E::GENERIC ? (p.mul != nullptr) : E::MUL;
+    const bool has_res = E::GENERIC ? (p.residual != nullptr) : E::RES;
+    // Pull a tile's multiplier / residual rows into L2 one tile ahead of its epilogue, so the epilogue's 128-bit
+    // loads are L2 hits instead of ~1 us DRAM round trips (they cannot be issued deep enough from registers).
+    auto prefetch_tile = [&](int t) {
+      if (!(has_mul || has_res) || t >= num_tiles) return;
+      const int row = (t / tiles_n) * GEMM_BM + et;
+      if (row >= p.M) return;
+      const int c0 = (t % tiles_n) * bn_out;
+      for (int c = 0; c < bn_out && c0 + c < n_out; c += 32) {
+        if (has_mul) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.mul + (size_t)row * p.ld_mul + c0 + c));
+        if (has_res) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.residual + (size_t)row * p.ld_res + c0 + c));
+      }
+    };
+    prefetch_tile(blockIdx.x);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      prefetch_tile(tile + gridDim.x);
       const int m0 = (tile / tiles_n) * GEMM_BM;
       const int tn = tile % tiles_n;
       const int n0 = tn * BN;

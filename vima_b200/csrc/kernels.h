@@ -69,6 +69,8 @@ cudaError_t launch_fill_ee(const long long* ee, const float* table, long long n_
 cudaError_t launch_action_scale(const long long* idx, long long n, int width, const float* inv_bins, float* out, cudaStream_t s);
 cudaError_t launch_head_select(const float* logits, int B, int n_heads, const int* head_off, float* logits_norm, long long* modes,
                                cudaStream_t s);
+cudaError_t launch_gato_positions(const unsigned char* prompt_mask, int B, int Lp, int L, unsigned char* mask_out, long long* pos_out,
+                                  cudaStream_t s);
 cudaError_t launch_max_u8(const unsigned char* x, long long n, int* out_max, cudaStream_t s);
 
 }  // namespace vima

@@ -296,6 +296,7 @@ cudaError_t launch_patchify(const unsigned char* img, long long N, int H, int W,
 }
 
 // x[n, 0] = cls + pos[0]; x[n, 1+p] = patch_out[n*(S-1)+p] + pos[1+p]   (vit.py:173-179)
+// cls == null (Gato ViT, vit.py:123-126): x[n, s] = patch_out[n*S+s] + pos[s]
 __global__ void vit_tokens_kernel(const float4* __restrict__ patch_out, const float4* __restrict__ cls, const float4* __restrict__ pos,
                                   long long N, int S, int W4, float4* __restrict__ out) {
   const long long total = N * S * W4;
@@ -304,7 +305,8 @@ __global__ void vit_tokens_kernel(const float4* __restrict__ patch_out, const fl
     const long long ns = i / W4;
     const int s = (int)(ns % S);
     const long long n = ns / S;
-    const float4 a = (s == 0) ? __ldg(cls + e) : __ldg(patch_out + (n * (S - 1) + (s - 1)) * W4 + e);
+    const float4 a = (cls == nullptr) ? __ldg(patch_out + ns * W4 + e)
+                                      : ((s == 0) ? __ldg(cls + e) : __ldg(patch_out + (n * (S - 1) + (s - 1)) * W4 + e));
     const float4 p = __ldg(pos + (size_t)s * W4 + e);
     out[i] = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
   }
@@ -413,6 +415,42 @@ cudaError_t launch_head_select(const float* logits, int B, int n_heads, const in
   if (B == 0) return cudaSuccess;
   const int warps = B * n_heads;
   head_select_kernel<<<(warps + 7) / 8, 256, 0, s>>>(logits, B, n_heads, head_off, logits_norm, modes);
+  return cudaGetLastError();
+}
+
+// Gato sequence layout (vima_gato_policy.py:150-182): mask = [prompt_mask | ones], position ids = arange over the
+// n valid prompt tokens, (n-1) on padded prompt slots, then n, n+1, ... for the separator + history.
+__global__ void gato_positions_kernel(const unsigned char* __restrict__ prompt_mask, int Lp, int L, unsigned char* __restrict__ mask_out,
+                                      long long* __restrict__ pos_out) {
+  __shared__ int n_valid_s;
+  const int b = blockIdx.x;
+  if (threadIdx.x == 0) n_valid_s = 0;
+  __syncthreads();
+  int cnt = 0;
+  for (int l = threadIdx.x; l < Lp; l += blockDim.x) cnt += prompt_mask[(size_t)b * Lp + l] != 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&n_valid_s, cnt);
+  __syncthreads();
+  const int n = n_valid_s;
+  for (int l = threadIdx.x; l < L; l += blockDim.x) {
+    long long id;
+    unsigned char m;
+    if (l < Lp) {
+      id = l < n ? l : n - 1;
+      m = prompt_mask[(size_t)b * Lp + l] != 0;
+    } else {
+      id = n + (l - Lp);
+      m = 1;
+    }
+    pos_out[(size_t)b * L + l] = id;
+    mask_out[(size_t)b * L + l] = m;
+  }
+}
+cudaError_t launch_gato_positions(const unsigned char* prompt_mask, int B, int Lp, int L, unsigned char* mask_out, long long* pos_out,
+                                  cudaStream_t s) {
+  if (B == 0) return cudaSuccess;
+  gato_positions_kernel<<<B, 256, 0, s>>>(prompt_mask, Lp, L, mask_out, pos_out);
   return cudaGetLastError();
 }
 

@@ -44,6 +44,33 @@ class ResidualAttentionBlock(nn.Module):
         self.ln_2 = nn.LayerNorm(d_model)
 
 
+def pack_vit_blocks(ctx, blocks, p):
+    return [{
+        "in": eng.pack_linear(ctx, blk.attn.in_proj_weight, blk.attn.in_proj_bias, transposed=False, p=p),
+        "out": eng.pack_linear(ctx, blk.attn.out_proj.weight, blk.attn.out_proj.bias, transposed=False, p=p),
+        "fc": eng.pack_linear(ctx, blk.mlp.c_fc.weight, blk.mlp.c_fc.bias, transposed=False, p=p),
+        "pr": eng.pack_linear(ctx, blk.mlp.c_proj.weight, blk.mlp.c_proj.bias, transposed=False, p=p),
+    } for blk in blocks]
+
+
+def run_vit_blocks(ctx, p, blocks, Wblocks, x32, y16, N, S, Wm, heads):
+    """Pre-LN residual blocks (vit.py:199-236). x32: residual stream [N*S, W] (updated in place by the GEMM epilogues),
+    y16: ln_1(x) of the first block as operands.  Returns the final residual stream."""
+    dev = x32.device
+    att16 = eng.Opnd(N * S, Wm, dev, p.split)
+    for i, (blk, Wb) in enumerate(zip(blocks, Wblocks)):
+        qkv32, _ = eng.gemm(ctx, y16, Wb["in"], p, want_f32=True)
+        ctx.small_attention(qkv32, N=N, S=S, H=heads, W=Wm, scale=1.0 / math.sqrt(Wm // heads), o_hi=att16.hi, o_lo=att16.lo, dtype=p.dtype)
+        eng.gemm(ctx, att16, Wb["out"], p, residual=x32, out_f32=x32)
+        _, _, y16 = eng.norm(ctx, x32, p, rows=N * S, cols=Wm, w=blk.ln_2.weight.detach(), b=blk.ln_2.bias.detach(), eps=blk.ln_2.eps, want16=True)
+        _, h16 = eng.gemm(ctx, y16, Wb["fc"], p, act=_C.ACT_QUICKGELU, want16=True)
+        eng.gemm(ctx, h16, Wb["pr"], p, residual=x32, out_f32=x32)
+        if i + 1 < len(blocks):
+            nb = blocks[i + 1]
+            _, _, y16 = eng.norm(ctx, x32, p, rows=N * S, cols=Wm, w=nb.ln_1.weight.detach(), b=nb.ln_1.bias.detach(), eps=nb.ln_1.eps, want16=True)
+    return x32
+
+
 class VisionTransformer(nn.Module):
     def __init__(self, resolution: int, patch_size: int, width: int, layers: int, heads: int, output_dim: int):
         super().__init__()
@@ -64,14 +91,7 @@ class VisionTransformer(nn.Module):
     def _packed(self, ctx, p):
         def build():
             W = {"conv": eng.pack_linear(ctx, self.conv1.weight.detach().reshape(self.width, -1), None, transposed=False, p=p),
-                 "proj": eng.pack_linear(ctx, self.projection, None, transposed=True, p=p), "blocks": []}
-            for blk in self.blocks:
-                W["blocks"].append({
-                    "in": eng.pack_linear(ctx, blk.attn.in_proj_weight, blk.attn.in_proj_bias, transposed=False, p=p),
-                    "out": eng.pack_linear(ctx, blk.attn.out_proj.weight, blk.attn.out_proj.bias, transposed=False, p=p),
-                    "fc": eng.pack_linear(ctx, blk.mlp.c_fc.weight, blk.mlp.c_fc.bias, transposed=False, p=p),
-                    "pr": eng.pack_linear(ctx, blk.mlp.c_proj.weight, blk.mlp.c_proj.bias, transposed=False, p=p),
-                })
+                 "proj": eng.pack_linear(ctx, self.projection, None, transposed=True, p=p), "blocks": pack_vit_blocks(ctx, self.blocks, p)}
             return W
 
         return self._wc.get("vit", tuple(self.parameters()), build)
@@ -96,17 +116,7 @@ class VisionTransformer(nn.Module):
         b0 = self.blocks[0]
         x32, _, y16 = eng.norm(ctx, tok32, p, rows=N * S, cols=Wm, w=self.ln_pre.weight.detach(), b=self.ln_pre.bias.detach(), eps=self.ln_pre.eps,
                                w2=b0.ln_1.weight.detach(), b2=b0.ln_1.bias.detach(), eps2=b0.ln_1.eps, want_f32=True, want16=True)
-        att16 = eng.Opnd(N * S, Wm, dev, p.split)
-        for i, (blk, Wb) in enumerate(zip(self.blocks, W["blocks"])):
-            qkv32, _ = eng.gemm(ctx, y16, Wb["in"], p, want_f32=True)
-            ctx.small_attention(qkv32, N=N, S=S, H=self.heads, W=Wm, scale=1.0 / math.sqrt(Wm // self.heads), o_hi=att16.hi, o_lo=att16.lo, dtype=p.dtype)
-            eng.gemm(ctx, att16, Wb["out"], p, residual=x32, out_f32=x32)
-            _, _, y16 = eng.norm(ctx, x32, p, rows=N * S, cols=Wm, w=blk.ln_2.weight.detach(), b=blk.ln_2.bias.detach(), eps=blk.ln_2.eps, want16=True)
-            _, h16 = eng.gemm(ctx, y16, Wb["fc"], p, act=_C.ACT_QUICKGELU, want16=True)
-            eng.gemm(ctx, h16, Wb["pr"], p, residual=x32, out_f32=x32)
-            if i + 1 < len(self.blocks):
-                nb = self.blocks[i + 1]
-                _, _, y16 = eng.norm(ctx, x32, p, rows=N * S, cols=Wm, w=nb.ln_1.weight.detach(), b=nb.ln_1.bias.detach(), eps=nb.ln_1.eps, want16=True)
+        x32 = run_vit_blocks(ctx, p, self.blocks, W["blocks"], x32, y16, N, S, Wm, self.heads)
         # ln_post on the CLS rows (row stride S*width), then @ projection
         _, _, cls16 = eng.norm(ctx, x32, p, rows=N, cols=Wm, ldx=S * Wm, w=self.ln_post.weight.detach(), b=self.ln_post.bias.detach(),
                                eps=self.ln_post.eps, want16=True)
@@ -206,3 +216,97 @@ class ObjEncoder(nn.Module):
             outs.append(o32.view(*lead, self._transformer_emb_dim))
             r0 += n
         return torch.cat(outs, dim=-2)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# VIMA-Gato baseline encoder (BASELINE.json configs[4]): whole 64x128 views, 32x32 patches, every patch token kept
+# ------------------------------------------------------------------------------------------------------------
+class GatoVisionTransformerRectangular(nn.Module):
+    """vit.py:85-134: no CLS token; ln_post and the projection apply to all patch tokens."""
+
+    def __init__(self, img_size, patch_size: int, width: int, layers: int, heads: int, output_dim: int):
+        super().__init__()
+        self.output_dim, self.width, self.heads = output_dim, width, heads
+        self._img_size, self._patch_size = tuple(img_size), patch_size
+        if width // heads != 32:
+            raise NotImplementedError("the fused small-sequence attention kernel is built for head_dim 32")
+        self.conv1 = nn.Conv2d(3, width, kernel_size=patch_size, stride=patch_size, bias=False)
+        scale = width ** -0.5
+        nh, nw = img_size[0] // patch_size, img_size[1] // patch_size
+        self.pos_embed = nn.Parameter(scale * torch.randn(nh * nw, width))
+        self.ln_pre = nn.LayerNorm(width)
+        self.blocks = nn.Sequential(*[ResidualAttentionBlock(width, heads) for _ in range(layers)])
+        self.ln_post = nn.LayerNorm(width)
+        self.projection = nn.Parameter(scale * torch.randn(width, output_dim))
+        self.img_patch_len = nh * nw
+        self._wc = eng.WeightCache()
+
+    def encode_u8(self, img_u8: torch.Tensor) -> torch.Tensor:
+        """(N,3,H,W) uint8 -> (N, n_patches, output_dim) fp32."""
+        ctx = eng.ctx_for(img_u8)
+        p = eng.prec()
+        N, C, H, Wd = img_u8.shape
+        assert (H, Wd) == self._img_size and C == 3
+        P, Wm, S = self._patch_size, self.width, self.img_patch_len
+        dev = img_u8.device
+        W = self._wc.get("gvit", tuple(self.parameters()), lambda: {
+            "conv": eng.pack_linear(ctx, self.conv1.weight.detach().reshape(Wm, -1), None, transposed=False, p=p),
+            "proj": eng.pack_linear(ctx, self.projection, None, transposed=True, p=p), "blocks": pack_vit_blocks(ctx, self.blocks, p)})
+        patches = eng.Opnd(N * S, 3 * P * P, dev, p.split)
+        ctx.patchify(img_u8.contiguous(), N, H, Wd, P, patches.hi, patches.lo, dtype=p.dtype)
+        pe32, _ = eng.gemm(ctx, patches, W["conv"], p, want_f32=True)
+        tok32 = torch.empty((N * S, Wm), dtype=torch.float32, device=dev)
+        ctx.vit_tokens(pe32, None, self.pos_embed.detach(), N, S, Wm, tok32)
+        b0 = self.blocks[0]
+        x32, _, y16 = eng.norm(ctx, tok32, p, rows=N * S, cols=Wm, w=self.ln_pre.weight.detach(), b=self.ln_pre.bias.detach(), eps=self.ln_pre.eps,
+                               w2=b0.ln_1.weight.detach(), b2=b0.ln_1.bias.detach(), eps2=b0.ln_1.eps, want_f32=True, want16=True)
+        x32 = run_vit_blocks(ctx, p, self.blocks, W["blocks"], x32, y16, N, S, Wm, self.heads)
+        _, _, post16 = eng.norm(ctx, x32, p, rows=N * S, cols=Wm, w=self.ln_post.weight.detach(), b=self.ln_post.bias.detach(), eps=self.ln_post.eps,
+                                want16=True)
+        out32, _ = eng.gemm(ctx, post16, W["proj"], p, want_f32=True)
+        return out32.view(N, S, self.output_dim)
+
+
+class GatoViTEncoder(nn.Module):
+    def __init__(self, *, img_size, patch_size: int, width: int, layers: int, heads: int, output_dim: int):
+        super().__init__()
+        self.output_dim = output_dim
+        self.vit = GatoVisionTransformerRectangular(img_size=img_size, patch_size=patch_size, width=width, layers=layers, heads=heads,
+                                                    output_dim=output_dim)
+
+    def forward(self, x: torch.Tensor):
+        """x: (..., 3, H, W) uint8 -> (..., L, E)   (vit.py:71-82)."""
+        assert x.dim() >= 4
+        if x.dtype != torch.uint8:
+            x = x.to(torch.uint8)
+        lead = x.shape[:-3]
+        out = self.vit.encode_u8(x.reshape(-1, *x.shape[-3:]))
+        return out.view(*lead, *out.shape[-2:])
+
+
+class GatoMultiViewRGBEncoder(nn.Module):
+    """obj_encoder.py:102-147: both views through the shared Gato ViT, patch tokens concatenated on the token axis."""
+
+    def __init__(self, *, emb_dim: int, views, img_size, vit_patch_size=None, vit_width=None, vit_layers=None, vit_heads=None):
+        super().__init__()
+        self._views = sorted(views)
+        self.output_dim = emb_dim
+        self.cropped_img_encoder = GatoViTEncoder(img_size=img_size, patch_size=vit_patch_size, width=vit_width, layers=vit_layers,
+                                                  heads=vit_heads, output_dim=emb_dim)
+
+    def forward(self, rgb):
+        views = self._views
+        xs = [rgb[v] if rgb[v].dtype == torch.uint8 else rgb[v].to(torch.uint8) for v in views]
+        lead = xs[0].shape[:-3]
+        n = [int(x.numel() // (x.shape[-3] * x.shape[-2] * x.shape[-1])) for x in xs]
+        allx = torch.cat([x.reshape(-1, *x.shape[-3:]) for x in xs], dim=0)  # one batched pass through the shared ViT
+        feats = self.cropped_img_encoder.vit.encode_u8(allx)
+        outs, r0 = [], 0
+        for k in n:
+            outs.append(feats[r0:r0 + k].view(*lead, *feats.shape[-2:]))
+            r0 += k
+        return torch.cat(outs, dim=-2)
+
+    @property
+    def img_patch_len(self):
+        return self.cropped_img_encoder.vit.img_patch_len * len(self._views)

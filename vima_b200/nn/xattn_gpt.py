@@ -52,6 +52,39 @@ class Block(nn.Module):
         self.ln_2 = nn.LayerNorm(nx, eps=eps)
 
 
+def pack_block(ctx, blk: "Block", p) -> dict:
+    return {
+        "c_attn": eng.pack_linear(ctx, blk.attn.c_attn.weight, blk.attn.c_attn.bias, transposed=True, p=p),
+        "c_proj": eng.pack_linear(ctx, blk.attn.c_proj.weight, blk.attn.c_proj.bias, transposed=True, p=p),
+        "fc_glu": eng.pack_glu(ctx, blk.mlp.c_fc.weight, blk.mlp.c_fc.bias, blk.mlp.gated_layer.weight, val_transposed=True,
+                               gate_transposed=False, p=p),
+        "mlp_proj": eng.pack_linear(ctx, blk.mlp.c_proj.weight, blk.mlp.c_proj.bias, transposed=True, p=p),
+    }
+
+
+def run_block(ctx, p, W, blk: "Block", x32, x16, c16, *, B, L, E, H, omask, chain_ln=None, want16=False, out_f32=None):
+    """GPT-1 post-LN block (components.py:23-37 / gpt.py:223-249): returns (LN2 output fp32, operands of the NEXT consumer):
+    with `chain_ln` the operands are chain_ln(LN2(...)) (next layer's query LayerNorm), with `want16` they are LN2(...) itself."""
+    M = B * L
+    d = E // H
+    _, qkv16 = eng.gemm(ctx, x16, W["c_attn"], p, want16=True)
+    ctx.attention(q=(qkv16.hi, qkv16.lo, qkv16.ld, 0), k=(qkv16.hi, qkv16.lo, qkv16.ld, E), v=(qkv16.hi, qkv16.lo, qkv16.ld, 2 * E),
+                  o=(c16.hi, c16.lo, c16.ld, 0), B=B, H=H, Lq=L, Lk=L, D=d, scale=1.0 / math.sqrt(d), causal=True, key_mask=omask, dtype=p.dtype)
+    s32, _ = eng.gemm(ctx, c16, W["c_proj"], p, residual=x32, want_f32=True)
+    n32, _, n16 = eng.norm(ctx, s32, p, rows=M, cols=E, w=blk.ln_1.weight.detach(), b=blk.ln_1.bias.detach(), eps=blk.ln_1.eps, want_f32=True,
+                           want16=True)
+    _, h16 = eng.gemm(ctx, n16, W["fc_glu"], p, act=_C.ACT_GELU, want16=True)
+    s32, _ = eng.gemm(ctx, h16, W["mlp_proj"], p, residual=n32, out_f32=s32)
+    del h16
+    w, b = blk.ln_2.weight.detach(), blk.ln_2.bias.detach()
+    if chain_ln is not None:
+        y32, _, nxt16 = eng.norm(ctx, s32, p, rows=M, cols=E, w=w, b=b, eps=blk.ln_2.eps, w2=chain_ln.weight.detach(), b2=chain_ln.bias.detach(),
+                                 eps2=chain_ln.eps, want16=True, out_f32=out_f32, want_f32=out_f32 is None)
+    else:
+        y32, _, nxt16 = eng.norm(ctx, s32, p, rows=M, cols=E, w=w, b=b, eps=blk.ln_2.eps, want16=want16, out_f32=out_f32, want_f32=out_f32 is None)
+    return y32, nxt16
+
+
 class XAttention(nn.Module):
     def __init__(self, dim: int, *, num_heads: int, ff_expanding: int, kv_n_positions: int, use_geglu: bool):
         super().__init__()
@@ -118,11 +151,7 @@ class XAttnGPT(nn.Module):
                 d["w1"] = eng.pack_linear(ctx, xa.linear1.weight, None, transposed=False, p=p)
                 d["wg"] = eng.pack_linear(ctx, xa.gated_layer.weight, None, transposed=False, p=p)
                 d["w2"] = eng.pack_linear(ctx, xa.linear2.weight, None, transposed=False, p=p)
-                d["c_attn"] = eng.pack_linear(ctx, blk.attn.c_attn.weight, blk.attn.c_attn.bias, transposed=True, p=p)
-                d["c_proj"] = eng.pack_linear(ctx, blk.attn.c_proj.weight, blk.attn.c_proj.bias, transposed=True, p=p)
-                d["fc_glu"] = eng.pack_glu(ctx, blk.mlp.c_fc.weight, blk.mlp.c_fc.bias, blk.mlp.gated_layer.weight,
-                                           val_transposed=True, gate_transposed=False, p=p)
-                d["mlp_proj"] = eng.pack_linear(ctx, blk.mlp.c_proj.weight, blk.mlp.c_proj.bias, transposed=True, p=p)
+                d.update(pack_block(ctx, blk, p))
                 L.append(d)
             return L
 
@@ -228,22 +257,78 @@ class XAttnGPT(nn.Module):
             xb32, xb16 = eng.gemm(ctx, h16, W["w2"], p, residual=a32, want_f32=True, want16=True)
             del h16, a32, a16
             # ---------------- causal Block ----------------
-            _, qkv16 = eng.gemm(ctx, xb16, W["c_attn"], p, want16=True)
-            ctx.attention(q=(qkv16.hi, qkv16.lo, qkv16.ld, 0), k=(qkv16.hi, qkv16.lo, qkv16.ld, E), v=(qkv16.hi, qkv16.lo, qkv16.ld, 2 * E),
-                          o=(c16.hi, c16.lo, c16.ld, 0), B=B, H=H, Lq=L, Lk=L, D=d_s, scale=1.0 / math.sqrt(d_s), causal=True,
-                          key_mask=omask, dtype=p.dtype)
-            s32, _ = eng.gemm(ctx, c16, W["c_proj"], p, residual=xb32, want_f32=True)
-            w, b = lnw(blk.ln_1)
-            n32, _, n16 = eng.norm(ctx, s32, p, rows=M, cols=E, w=w, b=b, eps=blk.ln_1.eps, want_f32=True, want16=True)
-            _, h16 = eng.gemm(ctx, n16, W["fc_glu"], p, act=_C.ACT_GELU, want16=True)
-            s32, _ = eng.gemm(ctx, h16, W["mlp_proj"], p, residual=n32, out_f32=s32)
-            del h16
-            w, b = lnw(blk.ln_2)
-            if i + 1 < self.n_layer:
-                nxt = self.xattns[i + 1].layernorm
-                x32, _, qin16 = eng.norm(ctx, s32, p, rows=M, cols=E, w=w, b=b, eps=blk.ln_2.eps, w2=nxt.weight.detach(), b2=nxt.bias.detach(),
-                                         eps2=nxt.eps, want16=True, out_f32=x32)
-            else:
-                x32, _, _ = eng.norm(ctx, s32, p, rows=M, cols=E, w=w, b=b, eps=blk.ln_2.eps, out_f32=x32)
+            nxt = self.xattns[i + 1].layernorm if i + 1 < self.n_layer else None
+            x32, qin16 = run_block(ctx, p, W, blk, xb32, xb16, c16, B=B, L=L, E=E, H=H, omask=omask, chain_ln=nxt, out_f32=x32)
+        out = x32.view(B, L, E)
+        return out if batch_first else out.transpose(0, 1)
+
+
+class _OpenAIGPTModel(nn.Module):
+    """Parameter holder with the key layout of the reference's OpenAIGPTModel (gpt.py:83-101)."""
+
+    def __init__(self, vocab_size, n_positions, n_embd, n_layer, n_head, geglu):
+        super().__init__()
+        self.tokens_embed = nn.Embedding(vocab_size, n_embd)
+        self.positions_embed = nn.Embedding(n_positions, n_embd)
+        self.h = nn.ModuleList([Block(n_embd, n_positions, n_head, geglu) for _ in range(n_layer)])
+        for blk in self.h:  # HF >= 4.3x keeps the causal buffer out of the state dict (checked against the reference here)
+            buf = blk.attn._buffers.pop("bias")
+            blk.attn.register_buffer("bias", buf, persistent=False)
+        self.register_buffer("position_ids", torch.arange(n_positions))
+
+
+class HFGPT(nn.Module):
+    """Decoder-only GPT-1 stack with GEGLU (reference: vima/nn/seq_modeling/gpt/gpt.py:15-301) -- the VIMA-Gato baseline's
+    sequence model.  Same Block kernels as XAttnGPT (causal-only path, BASELINE.json configs[4])."""
+
+    def __init__(self, *, vocab_size=40478, n_positions=512, n_embd=768, n_layer=12, n_head=12, dropout: float = 0.1, use_geglu: bool = False):
+        super().__init__()
+        if not use_geglu:
+            raise NotImplementedError("vima_b200.HFGPT implements the GEGLU configuration VIMA-Gato uses")
+        self.n_embd, self.n_layer, self.n_head, self.n_positions = n_embd, n_layer, n_head, n_positions
+        self.lm = _OpenAIGPTModel(vocab_size, n_positions, n_embd, n_layer, n_head, use_geglu)
+        for m in self.modules():
+            if isinstance(m, (nn.Linear, nn.Embedding)):
+                nn.init.normal_(m.weight, std=0.02)
+        self._wc = eng.WeightCache()
+        # checkpoints written with transformers 4.x carry `lm.h.N.attn.bias`; accept and ignore it
+        self._register_load_state_dict_pre_hook(self._drop_causal_buffers)
+
+    @staticmethod
+    def _drop_causal_buffers(state_dict, prefix, *args):
+        for k in [k for k in state_dict if k.startswith(prefix + "lm.h.") and k.endswith(".attn.bias")]:
+            del state_dict[k]
+
+    def forward(self, x: torch.Tensor, *, custom_mask: Optional[torch.Tensor] = None, position_ids: Optional[torch.Tensor] = None,
+                batch_first: bool = False):
+        """x: (L,B,E) if not batch_first else (B,L,E); custom_mask (B,L) or (B,1,L) combined with the causal mask (gpt.py:46-79)."""
+        ctx = eng.ctx_for(x)
+        p = eng.prec()
+        if batch_first:
+            B, L, E = x.shape
+        else:
+            L, B, E = x.shape
+        assert E == self.n_embd and L <= self.n_positions
+        dev = x.device
+        xf = x.float()
+        if xf.stride(-1) != 1:
+            xf = xf.contiguous()
+        sb, sl = (xf.stride(0), xf.stride(1)) if batch_first else (xf.stride(1), xf.stride(0))
+        if position_ids is None:
+            position_ids = self.lm.position_ids[None, :L].expand(B, L)
+        ids = position_ids.to(torch.int64).contiguous()
+        omask = None
+        if custom_mask is not None:
+            if custom_mask.dim() == 3:
+                custom_mask = custom_mask.squeeze(dim=1)
+            omask = eng.as_u8(custom_mask != 0)
+        M, H = B * L, self.n_head
+        x32 = torch.empty((M, E), dtype=torch.float32, device=dev)
+        x16 = eng.Opnd(M, E, dev, p.split)
+        ctx.add_pos_embed(xf, sb, sl, ids, self.lm.positions_embed.weight.detach(), B, L, E, out_f32=x32, hi=x16.hi, lo=x16.lo, dtype=p.dtype)
+        layers = self._wc.get("blocks", tuple(self.lm.h.parameters()), lambda: [pack_block(ctx, blk, p) for blk in self.lm.h])
+        c16 = eng.Opnd(M, E, dev, p.split)
+        for i, (blk, W) in enumerate(zip(self.lm.h, layers)):
+            x32, x16 = run_block(ctx, p, W, blk, x32, x16, c16, B=B, L=L, E=E, H=H, omask=omask, want16=i + 1 < self.n_layer)
         out = x32.view(B, L, E)
         return out if batch_first else out.transpose(0, 1)

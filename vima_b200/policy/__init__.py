@@ -1,1 +1,2 @@
 from .vima_policy import VIMAPolicy
+from .vima_gato_policy import VIMAGatoPolicy
