@@ -29,30 +29,39 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
 }
 
 template <int DT>
-__device__ __forceinline__ void pack_split(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-  unsigned short h0, l0, h1, l1;
-  split16<DT>(x0, h0, l0);
-  split16<DT>(x1, h1, l1);
-  hi = (uint32_t)h0 | ((uint32_t)h1 << 16);
-  lo = (uint32_t)l0 | ((uint32_t)l1 << 16);
+__device__ __forceinline__ void pack_split(float x0, float x1, uint32_t& hi, uint32_t& lo) { split2<DT>(x0, x1, hi, lo); }
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row_ptr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(smem_row_ptr)));
 }
+
+// Scores are kept in the log2 domain: y = s * (scale*log2e) [+ bias*log2e]; the soft causal constant becomes
+// -1e4*log2e; the key-mask constant stays finfo.min (any value + finfo.min rounds to finfo.min, so "all masked keys are
+// equal" -- the reference's degenerate uniform row -- is preserved). softmax is invariant to the common factor.
+constexpr float CAUSAL_L2 = -1e4f * LOG2E;
+constexpr float EXIT_L2 = -9000.f * LOG2E;
 
 template <int D, int DT, bool SPLIT>
 __global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
   constexpr int KS = D / 16;   // k-steps over head_dim for Q K^T
   constexpr int ND = D / 8;    // n-tiles over head_dim for P V
-  constexpr int KROW = D + 8;  // padded smem row (halfs) -> conflict-free 32-bit fragment loads
+  constexpr int KROW = D + 8;  // padded smem row (halfs) -> conflict-free ldmatrix
   extern __shared__ __align__(16) unsigned char smem[];
   const int h = blockIdx.x, b = blockIdx.y;
   const int Lk = p.Lk, Lq = p.Lq;
   const int Lk_pad = (Lk + 63) & ~63;
   const int VROW = Lk_pad + 8;
+  const int n_kt = Lk_pad / 64;
   unsigned short* Ks_hi = reinterpret_cast<unsigned short*>(smem);
   unsigned short* Ks_lo = Ks_hi + (SPLIT ? Lk_pad * KROW : 0);
   unsigned short* Vt_hi = Ks_lo + Lk_pad * KROW;
   unsigned short* Vt_lo = Vt_hi + (SPLIT ? D * VROW : 0);
   float* maskadd = reinterpret_cast<float*>(Vt_lo + D * VROW);
-  float* sbias = maskadd + Lk_pad;  // [2*Lk-1] when rel_bias
+  int* tile_plain = reinterpret_cast<int*>(maskadd + Lk_pad);  // [n_kt] 1 = every key of the tile is real and unmasked
+  int* qb_counter = tile_plain + n_kt;
+  float* sbias = reinterpret_cast<float*>(qb_counter + 1);     // [2*Lk-1] (log2 domain) when rel_bias
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // ---- stage K (row-major) and V (transposed) of this (b, h) in shared memory ----
@@ -86,13 +95,27 @@ __global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
     maskadd[j] = m;
   }
   if (p.rel_bias)
-    for (int j = tid; j < 2 * Lk - 1; j += 256) sbias[j] = __ldg(p.rel_bias + (size_t)h * (2 * Lk - 1) + j);
+    for (int j = tid; j < 2 * Lk - 1; j += 256) sbias[j] = __ldg(p.rel_bias + (size_t)h * (2 * Lk - 1) + j) * LOG2E;
+  if (tid == 0) *qb_counter = 0;
+  __syncthreads();
+  for (int kt = warp; kt < n_kt; kt += 8) {
+    const bool ok = (maskadd[kt * 64 + lane] == 0.f) && (maskadd[kt * 64 + 32 + lane] == 0.f);
+    const bool all_ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) tile_plain[kt] = all_ok ? 1 : 0;
+  }
   __syncthreads();
 
   const int g = lane >> 2, t = lane & 3;
   const int n_qb = (Lq + 15) / 16;
-  const int n_kt = Lk_pad / 64;
-  for (int qb = warp; qb < n_qb; qb += 8) {
+  const float c_l2 = p.scale * LOG2E;
+  const int lm_row = lane & 7, lm_chunk = (lane >> 3) * 8;  // ldmatrix: row within the 8x8 matrix, which of the 4 matrices
+  for (;;) {
+    // dynamic work distribution over 16-row query blocks, longest (latest, under the causal mask) first
+    int ticket = 0;
+    if (lane == 0) ticket = atomicAdd(qb_counter, 1);
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    if (ticket >= n_qb) break;
+    const int qb = n_qb - 1 - ticket;
     const int r0 = qb * 16 + g, r1 = r0 + 8;
     uint32_t qh[KS][4], ql[KS][4];
 #pragma unroll
@@ -121,34 +144,50 @@ __global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
         s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-        const int key = kt * 64 + nt * 8 + g;
+        const int key = kt * 64 + nt * 8 + lm_row;
 #pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-          const unsigned short* kp = Ks_hi + key * KROW + ks * 16 + 2 * t;
-          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kp);
-          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kp + 8);
-          mma16816<DT>(s[nt], qh[ks], b0, b1);
+        for (int kk = 0; kk < KS; kk += 2) {  // one ldmatrix.x4 = B fragments of two k-steps (32 head-dim columns)
+          uint32_t bh[4], bl[4];
+          ldmatrix_x4(bh, Ks_hi + key * KROW + kk * 16 + lm_chunk);
+          mma16816<DT>(s[nt], qh[kk], bh[0], bh[1]);
+          mma16816<DT>(s[nt], qh[kk + 1], bh[2], bh[3]);
           if (SPLIT) {
-            mma16816<DT>(s[nt], ql[ks], b0, b1);
-            const unsigned short* kq = Ks_lo + key * KROW + ks * 16 + 2 * t;
-            mma16816<DT>(s[nt], qh[ks], *reinterpret_cast<const uint32_t*>(kq), *reinterpret_cast<const uint32_t*>(kq + 8));
+            mma16816<DT>(s[nt], ql[kk], bh[0], bh[1]);
+            mma16816<DT>(s[nt], ql[kk + 1], bh[2], bh[3]);
+            ldmatrix_x4(bl, Ks_lo + key * KROW + kk * 16 + lm_chunk);
+            mma16816<DT>(s[nt], qh[kk], bl[0], bl[1]);
+            mma16816<DT>(s[nt], qh[kk + 1], bl[2], bl[3]);
           }
         }
       }
-      // ---- scale, bias, soft causal mask, key mask; row max ----
+      // ---- log2-domain scores; bias / soft causal mask / key mask only where the tile needs them ----
+      const bool needs_mask = !tile_plain[kt];
+      const bool needs_causal = p.causal && (kt * 64 + 63 > qb * 16);
       float mx[2] = {-INFINITY, -INFINITY};
+      if (!needs_mask && !needs_causal && p.rel_bias == nullptr) {
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
+        for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int j = kt * 64 + nt * 8 + 2 * t + (e & 1);
-          const int i = (e & 2) ? r1 : r0;
-          float x = s[nt][e] * p.scale;
-          if (p.rel_bias && j < Lk) x += sbias[j - min(i, Lq - 1) + Lk - 1];
-          if (p.causal && j > i) x = -1e4f;
-          x += maskadd[j];
-          s[nt][e] = x;
-          mx[e >> 1] = fmaxf(mx[e >> 1], x);
+          for (int e = 0; e < 4; ++e) {
+            const float y = s[nt][e] * c_l2;
+            s[nt][e] = y;
+            mx[e >> 1] = fmaxf(mx[e >> 1], y);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = kt * 64 + nt * 8 + 2 * t + (e & 1);
+            const int i = (e & 2) ? r1 : r0;
+            float y = s[nt][e] * c_l2;
+            if (p.rel_bias && j < Lk) y += sbias[j - min(i, Lq - 1) + Lk - 1];
+            if (needs_causal && j > i) y = CAUSAL_L2;
+            if (needs_mask) y += maskadd[j];
+            s[nt][e] = y;
+            mx[e >> 1] = fmaxf(mx[e >> 1], y);
+          }
         }
       }
       float corr[2];
@@ -157,7 +196,7 @@ __global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
         mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
         mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
         const float m_new = fmaxf(mrow[r], mx[r]);
-        corr[r] = exp2f((mrow[r] - m_new) * LOG2E);
+        corr[r] = ex2_approx(mrow[r] - m_new);
         mrow[r] = m_new;
         lrow[r] *= corr[r];
       }
@@ -166,7 +205,7 @@ __global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
       for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float pv = exp2f((s[nt][e] - mrow[e >> 1]) * LOG2E);
+          const float pv = ex2_approx(s[nt][e] - mrow[e >> 1]);
           s[nt][e] = pv;
           ps[e >> 1] += pv;
         }
@@ -179,31 +218,36 @@ __global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
         o[n][2] *= corr[1]; o[n][3] *= corr[1];
       }
       // ---- O += P V ----
+      uint32_t ph[4][4], pl[4][4];
 #pragma unroll
       for (int k2 = 0; k2 < 4; ++k2) {
-        uint32_t ph[4], pl[4];
-        pack_split<DT>(s[2 * k2][0], s[2 * k2][1], ph[0], pl[0]);
-        pack_split<DT>(s[2 * k2][2], s[2 * k2][3], ph[1], pl[1]);
-        pack_split<DT>(s[2 * k2 + 1][0], s[2 * k2 + 1][1], ph[2], pl[2]);
-        pack_split<DT>(s[2 * k2 + 1][2], s[2 * k2 + 1][3], ph[3], pl[3]);
-        const int k0 = kt * 64 + k2 * 16 + 2 * t;
+        pack_split<DT>(s[2 * k2][0], s[2 * k2][1], ph[k2][0], pl[k2][0]);
+        pack_split<DT>(s[2 * k2][2], s[2 * k2][3], ph[k2][1], pl[k2][1]);
+        pack_split<DT>(s[2 * k2 + 1][0], s[2 * k2 + 1][1], ph[k2][2], pl[k2][2]);
+        pack_split<DT>(s[2 * k2 + 1][2], s[2 * k2 + 1][3], ph[k2][3], pl[k2][3]);
+      }
 #pragma unroll
-        for (int n = 0; n < ND; ++n) {
-          const unsigned short* vp = Vt_hi + (n * 8 + g) * VROW + k0;
-          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vp);
-          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(vp + 8);
-          mma16816<DT>(o[n], ph, b0, b1);
+      for (int n = 0; n < ND; ++n) {
+        const int drow = n * 8 + lm_row;
+#pragma unroll
+        for (int kp = 0; kp < 2; ++kp) {  // one ldmatrix.x4 = V^T fragments of two 16-key steps
+          uint32_t vh4[4], vl4[4];
+          ldmatrix_x4(vh4, Vt_hi + drow * VROW + kt * 64 + kp * 32 + lm_chunk);
+          mma16816<DT>(o[n], ph[2 * kp], vh4[0], vh4[1]);
+          mma16816<DT>(o[n], ph[2 * kp + 1], vh4[2], vh4[3]);
           if (SPLIT) {
-            mma16816<DT>(o[n], pl, b0, b1);
-            const unsigned short* vq = Vt_lo + (n * 8 + g) * VROW + k0;
-            mma16816<DT>(o[n], ph, *reinterpret_cast<const uint32_t*>(vq), *reinterpret_cast<const uint32_t*>(vq + 8));
+            mma16816<DT>(o[n], pl[2 * kp], vh4[0], vh4[1]);
+            mma16816<DT>(o[n], pl[2 * kp + 1], vh4[2], vh4[3]);
+            ldmatrix_x4(vl4, Vt_lo + drow * VROW + kt * 64 + kp * 32 + lm_chunk);
+            mma16816<DT>(o[n], ph[2 * kp], vl4[0], vl4[1]);
+            mma16816<DT>(o[n], ph[2 * kp + 1], vl4[2], vl4[3]);
           }
         }
       }
       // Every later key tile is causally masked for all 16 rows: its weights are exp(-1e4 - m), exactly 0 in
       // fp32 once m > -1e4 + 104, so stopping here is bit-identical to the reference's full-width softmax.
       if (p.causal && (kt + 1) * 64 > qb * 16 + 15) {
-        const bool done = (mrow[0] > -9000.f) && (mrow[1] > -9000.f);
+        const bool done = (mrow[0] > EXIT_L2) && (mrow[1] > EXIT_L2);
         if (__all_sync(0xffffffffu, done)) break;
       }
     }
@@ -238,7 +282,7 @@ template <int D, int DT, bool SPLIT>
 static cudaError_t launch_attn_t(const AttnParams& p, cudaStream_t stream) {
   const int Lk_pad = (p.Lk + 63) & ~63;
   const size_t parts = SPLIT ? 2 : 1;
-  size_t smem = parts * (size_t)Lk_pad * (D + 8) * 2 + parts * (size_t)D * (Lk_pad + 8) * 2 + (size_t)Lk_pad * 4;
+  size_t smem = parts * (size_t)Lk_pad * (D + 8) * 2 + parts * (size_t)D * (Lk_pad + 8) * 2 + (size_t)Lk_pad * 4 + (size_t)(Lk_pad / 64 + 1) * 4;
   if (p.rel_bias) smem += (size_t)(2 * p.Lk) * 4;
   auto kern = attention_kernel<D, DT, SPLIT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

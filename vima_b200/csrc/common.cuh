@@ -51,6 +51,26 @@ __device__ __forceinline__ void split16_rt(int dt, float x, unsigned short& hi, 
   if (dt == DT_F16) split16<DT_F16>(x, hi, lo); else split16<DT_BF16>(x, hi, lo);
 }
 
+// Packed pair split: two F2FP (saturating, so |x| > 65504 degrades instead of producing inf/NaN) + one unpack.
+// Low 16 bits = first element.  3 instructions per element instead of 7 for the scalar form.
+template <int DT>
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  if constexpr (DT == DT_F16) {
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - hf.y), "f"(x0 - hf.x));
+  } else {
+    asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+    const float2 hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hi));
+    asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - hf.y), "f"(x0 - hf.x));
+  }
+}
+template <int DT>
+__device__ __forceinline__ void split4v(const float4& y, uint2& hi, uint2& lo) {
+  split2<DT>(y.x, y.y, hi.x, lo.x);
+  split2<DT>(y.z, y.w, hi.y, lo.y);
+}
+
 // ---------------------------------------------------------------------------------------------
 // activations
 // ---------------------------------------------------------------------------------------------

@@ -72,12 +72,7 @@ __device__ __forceinline__ float act_ct(float x) {
 }
 
 template <int DT>
-__device__ __forceinline__ void split4(const float4& y, uint2& hi, uint2& lo) {
-  unsigned short h0, h1, h2, h3, l0, l1, l2, l3;
-  split16<DT>(y.x, h0, l0); split16<DT>(y.y, h1, l1); split16<DT>(y.z, h2, l2); split16<DT>(y.w, h3, l3);
-  hi = make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
-  lo = make_uint2((uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2 | ((uint32_t)l3 << 16));
-}
+__device__ __forceinline__ void split4(const float4& y, uint2& hi, uint2& lo) { split4v<DT>(y, hi, lo); }
 
 // One accumulator tile (this warp's 32 rows): TMEM -> registers (row per thread) -> bias/act/GLU -> smem transpose
 // -> [rows of 4 x 8 lanes x float4] -> mul / residual / stores, all 128-bit and coalesced.
@@ -93,6 +88,17 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_ro
   const int sub = lane >> 3;        // row within a group of 4
   const int c4 = (lane & 7) * 4;    // first of this lane's 4 columns inside the 32-column chunk
   for (int j = 0; j < bn_out; j += 32) {
+    // issue this chunk's multiplier / residual loads first: they fly while the accumulator is read and activated
+    const int col = tn * bn_out + j + c4;
+    const bool col_ok = col < n_out;  // n_out % 4 == 0 (checked on the host)
+    float4 mm[8], rr[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = row_base + it * 4 + sub;
+      const bool ok = col_ok && row < p.M;
+      if (has_mul) mm[it] = ok ? __ldg(reinterpret_cast<const float4*>(p.mul + (size_t)row * p.ld_mul + col)) : make_float4(1.f, 1.f, 1.f, 1.f);
+      if (has_res) rr[it] = ok ? __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)row * p.ld_res + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     uint32_t v[32];
     tmem_ld_32x32(t_row + j, v);
     float x[32];
@@ -128,16 +134,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_ro
 #pragma unroll
     for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(st + lane * GEMM_ST_LD + i) = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
     __syncwarp();
-    const int col = tn * bn_out + j + c4;
-    const bool col_ok = col < n_out;  // n_out % 4 == 0 (checked on the host)
-    float4 y[8], mm[8], rr[8];
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {  // issue every global load of the chunk before the first use
-      const int row = row_base + it * 4 + sub;
-      const bool ok = col_ok && row < p.M;
-      if (has_mul) mm[it] = ok ? __ldg(reinterpret_cast<const float4*>(p.mul + (size_t)row * p.ld_mul + col)) : make_float4(1.f, 1.f, 1.f, 1.f);
-      if (has_res) rr[it] = ok ? __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)row * p.ld_res + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    float4 y[8];
 #pragma unroll
     for (int it = 0; it < 8; ++it) y[it] = *reinterpret_cast<const float4*>(st + (it * 4 + sub) * GEMM_ST_LD + c4);
 #pragma unroll

@@ -190,11 +190,11 @@ __global__ void add_pos_embed_kernel(const float* __restrict__ tok, long long st
     const float4 v = make_float4(a.x + pz.x, a.y + pz.y, a.z + pz.z, a.w + pz.w);
     if (out_f32) reinterpret_cast<float4*>(out_f32)[i] = v;
     if (hi) {
-      unsigned short h0, h1, h2, h3, l0, l1, l2, l3;
-      split16<DT>(v.x, h0, l0); split16<DT>(v.y, h1, l1); split16<DT>(v.z, h2, l2); split16<DT>(v.w, h3, l3);
+      uint2 hv, lv;
+      split4v<DT>(v, hv, lv);
       const size_t o = (size_t)bl * ld16 + (size_t)e * 4;
-      *reinterpret_cast<uint2*>(hi + o) = make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
-      if (lo) *reinterpret_cast<uint2*>(lo + o) = make_uint2((uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2 | ((uint32_t)l3 << 16));
+      *reinterpret_cast<uint2*>(hi + o) = hv;
+      if (lo) *reinterpret_cast<uint2*>(lo + o) = lv;
     }
   }
 }
@@ -275,11 +275,11 @@ __global__ void patchify_kernel(const unsigned char* __restrict__ img, long long
     const float mean = c_img_mean[c], sd = c_img_std[c];
     const float f0 = ((float)u.x / 255.0f - mean) / sd, f1 = ((float)u.y / 255.0f - mean) / sd;
     const float f2 = ((float)u.z / 255.0f - mean) / sd, f3 = ((float)u.w / 255.0f - mean) / sd;
-    unsigned short h0, h1, h2, h3, l0, l1, l2, l3;
-    split16<DT>(f0, h0, l0); split16<DT>(f1, h1, l1); split16<DT>(f2, h2, l2); split16<DT>(f3, h3, l3);
+    uint2 hv, lv;
+    split4v<DT>(make_float4(f0, f1, f2, f3), hv, lv);
     const size_t o = (size_t)prow * ld16 + k;
-    *reinterpret_cast<uint2*>(hi + o) = make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
-    if (lo) *reinterpret_cast<uint2*>(lo + o) = make_uint2((uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2 | ((uint32_t)l3 << 16));
+    *reinterpret_cast<uint2*>(hi + o) = hv;
+    if (lo) *reinterpret_cast<uint2*>(lo + o) = lv;
   }
 }
 

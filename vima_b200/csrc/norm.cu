@@ -98,13 +98,10 @@ __global__ void __launch_bounds__(256) norm_rows_kernel(const NormParams p) {
     for (int i = 0; i < NORM_MAX_V4; ++i) {
       const int c = i * 32 + lane;
       if (c < nv4) {
-        unsigned short h0, h1, h2_, h3, l0, l1, l2_, l3;
-        split16<DT>(v[i].x, h0, l0);
-        split16<DT>(v[i].y, h1, l1);
-        split16<DT>(v[i].z, h2_, l2_);
-        split16<DT>(v[i].w, h3, l3);
-        h2[c] = make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2_ | ((uint32_t)h3 << 16));
-        if (l2) l2[c] = make_uint2((uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2_ | ((uint32_t)l3 << 16));
+        uint2 hv, lv;
+        split4v<DT>(v[i], hv, lv);
+        h2[c] = hv;
+        if (l2) l2[c] = lv;
       }
     }
   }
