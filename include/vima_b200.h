@@ -29,7 +29,7 @@ extern "C" {
 #endif
 #pragma GCC visibility push(default)
 
-#define VIMA_B200_ABI_VERSION 1
+#define VIMA_B200_ABI_VERSION 2
 
 enum { VIMA_OK = 0, VIMA_E_INVALID = 1, VIMA_E_CUDA = 2, VIMA_E_UNSUPPORTED = 3 };
 enum { VIMA_DT_F16 = 0, VIMA_DT_BF16 = 1 };
@@ -54,6 +54,9 @@ int vima_split_f32(vima_ctx*, const float* x, int64_t rows, int cols, int ldx, v
  * HF:pytorch_utils.py:97-123).  Output: K-major (hi, lo|NULL) [n, ld16], zero padded, multiplied by `scale`. */
 int vima_pack_weight(vima_ctx*, const float* w, int n, int k, int transposed, int ldw, void* hi, void* lo, int ld16, float scale,
                      int dtype, void* stream);
+/* Same source, e4m3 cross-term views for the "f16f8" GEMM mode: hi8 = e4m3(w*scale*2^-10), lo8 = e4m3((w*scale - f16(w*scale))*2^3). */
+int vima_pack_weight_f8(vima_ctx*, const float* w, int n, int k, int transposed, int ldw, void* hi8, void* lo8, int ld8, float scale,
+                        void* stream);
 
 /* ---- tcgen05 GEMM: out = epilogue(A[M,K] * B[N,K]^T) ------------------------------------------------------
  * Replaces every large Linear / Conv1D on the path: components.py:87-88,130-142 (c_attn, c_proj, c_fc, query,
@@ -83,6 +86,15 @@ typedef struct {
   void *out_hi, *out_lo; /* 16-bit outputs or NULL */
   int ld_o16;
   int block_n;           /* 0 = choose */
+  /* "f16f8" mode (fp16 operands only): fp16 hi*hi plus two e4m3 cross terms at the fp8 rate. a_lo8 = e4m3((a-a_hi)*2^10),
+   * a_hi8 = e4m3(a*2^-3), b_hi8 = e4m3(b*2^-10), b_lo8 = e4m3((b-b_hi)*2^3); [rows, ld8] bytes, ld8 % 16 == 0.  Set all four
+   * (and leave a_lo / b_lo NULL) to select it.  out_lo8 / out_hi8 make the epilogue emit the same views of its output. */
+  const void *a_lo8, *a_hi8;
+  int lda8;
+  const void *b_hi8, *b_lo8;
+  int ldb8;
+  void *out_lo8, *out_hi8;
+  int ld_o8;
 } vima_gemm_desc;
 int vima_gemm(vima_ctx*, const vima_gemm_desc* d, void* stream);
 /* Accumulator tile width the GLU weight interleave must use for an output width of n_out columns. */
@@ -114,6 +126,7 @@ typedef struct {
   float* out2_f32; int ld_o2;
   void *out_hi, *out_lo; int ld_o16;
   int dtype;
+  void *out_lo8, *out_hi8; int ld_o8; /* optional e4m3 cross-term views of the last norm's output (fp16 format) */
 } vima_norm_desc;
 int vima_norm(vima_ctx*, const vima_norm_desc* d, void* stream);
 
@@ -133,6 +146,7 @@ typedef struct {
   float scale;
   int causal;
   int dtype;
+  void *o_lo8, *o_hi8; int ldo8; /* optional e4m3 cross-term views of the output */
 } vima_attn_desc;
 int vima_attention(vima_ctx*, const vima_attn_desc* d, void* stream);
 
@@ -152,6 +166,8 @@ int vima_mask_cumsum(vima_ctx*, const uint8_t* mask, int B, int L, int64_t* pos,
  * ids set *err_flag (device int) to 1 -- the reference raises IndexError there. */
 int vima_add_pos_embed(vima_ctx*, const float* tok, int64_t stride_b, int64_t stride_l, const int64_t* ids, const float* table, int n_pos,
                        int B, int L, int E, float* out_f32, void* hi, void* lo, int ld16, int dtype, int* err_flag, void* stream);
+/* fp32 [rows, cols] -> e4m3 cross-term views (lo8 relative to the fp16 hi part, hi8), [rows, ld8] bytes. cols % 4 == 0. */
+int vima_split_f8(vima_ctx*, const float* x, int64_t rows, int cols, int ldx, void* lo8, void* hi8, int ld8, void* stream);
 /* vima_policy.py:180-233: prompt gather driven by a (kind, index) map per (b, position), see misc.cu. */
 int vima_gather_prompt(vima_ctx*, const int32_t* kind, const int32_t* index, const int64_t* word_ids, const float* word_table,
                        const float* img_emb, const uint8_t* img_mask, int B, int Lp, int D, float* out, uint8_t* mask_out, void* stream);

@@ -101,6 +101,19 @@ int vima_pack_weight(vima_ctx* c, const float* w, int n, int k, int transposed, 
            "pack_weight");
 }
 
+int vima_pack_weight_f8(vima_ctx* c, const float* w, int n, int k, int transposed, int ldw, void* hi8, void* lo8, int ld8, float scale, void* stream) {
+  CHECK_CTX(c);
+  if (!w || !hi8 || !lo8 || ld8 < k || (ld8 & 15)) return fail(c, VIMA_E_INVALID, "pack_weight_f8: ld8 must be >= k and a multiple of 16");
+  LAUNCHED(c, launch_pack_weight_f8(w, n, k, transposed, ldw, (unsigned char*)hi8, (unsigned char*)lo8, ld8, scale, (cudaStream_t)stream),
+           "pack_weight_f8");
+}
+
+int vima_split_f8(vima_ctx* c, const float* x, int64_t rows, int cols, int ldx, void* lo8, void* hi8, int ld8, void* stream) {
+  CHECK_CTX(c);
+  if (!x || !lo8 || !hi8 || (cols & 3) || (ldx & 3) || (ld8 & 3) || ld8 < cols) return fail(c, VIMA_E_INVALID, "split_f8: bad arguments");
+  LAUNCHED(c, launch_split_f8(x, rows, cols, ldx, (unsigned char*)lo8, (unsigned char*)hi8, ld8, (cudaStream_t)stream), "split_f8");
+}
+
 static int choose_block_n(int N, int glu) {
   const int step = glu ? 64 : 32;
   int best = step, best_pad = 1 << 30;
@@ -111,6 +124,19 @@ static int choose_block_n(int N, int glu) {
   return best;
 }
 int vima_glu_block_n(int n_out) { return choose_block_n(2 * n_out, 1); }
+
+// fp8 operand tile: rows of 64 bytes (64 K-elements), 64-byte swizzle
+static int make_tmap_f8(vima_ctx* c, CUtensorMap* tm, const void* base, int rows, int cols, int ld, int box_rows) {
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld};
+  const cuuint32_t box[2] = {(cuuint32_t)GEMM_BK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = ((PFN_encodeTiled)c->encode_tiled)(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(c, VIMA_E_CUDA, "cuTensorMapEncodeTiled(fp8) failed (%d): rows %d cols %d ld %d box %d", (int)r, rows, cols, ld, box_rows);
+  return VIMA_OK;
+}
 
 static int make_tmap(vima_ctx* c, CUtensorMap* tm, const void* base, int dtype, int rows, int cols, int ld, int box_rows) {
   const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -132,6 +158,16 @@ int vima_gemm(vima_ctx* c, const vima_gemm_desc* d, void* stream) {
   if ((d->lda & 7) || (d->ldb & 7) || ((uintptr_t)d->a_hi & 15) || ((uintptr_t)d->b_hi & 15))
     return fail(c, VIMA_E_INVALID, "gemm: operands need 16-byte aligned bases and ld %% 8 == 0 (lda %d ldb %d)", d->lda, d->ldb);
   if ((d->a_lo == nullptr) != (d->b_lo == nullptr)) return fail(c, VIMA_E_INVALID, "gemm: a_lo and b_lo must both be set or both be null");
+  const bool f8 = d->a_lo8 || d->a_hi8 || d->b_hi8 || d->b_lo8;
+  if (f8) {
+    if (!(d->a_lo8 && d->a_hi8 && d->b_hi8 && d->b_lo8) || d->a_lo || d->dtype != DT_F16)
+      return fail(c, VIMA_E_INVALID, "gemm: f16f8 mode needs all four e4m3 operands, fp16 hi operands and no 16-bit lo operands");
+    if ((d->lda8 & 15) || (d->ldb8 & 15) || ((uintptr_t)d->a_lo8 & 15) || ((uintptr_t)d->a_hi8 & 15) || ((uintptr_t)d->b_hi8 & 15) ||
+        ((uintptr_t)d->b_lo8 & 15) || d->lda8 < d->K || d->ldb8 < d->K)
+      return fail(c, VIMA_E_INVALID, "gemm: e4m3 operands need 16-byte aligned bases and ld %% 16 == 0");
+  }
+  if ((d->out_lo8 == nullptr) != (d->out_hi8 == nullptr) || (d->out_lo8 && (!d->out_hi || d->dtype != DT_F16 || (d->ld_o8 & 3))))
+    return fail(c, VIMA_E_INVALID, "gemm: out_lo8/out_hi8 come together, with an fp16 out_hi, ld_o8 %% 4 == 0");
   if (d->lda < d->K || d->ldb < d->K) return fail(c, VIMA_E_INVALID, "gemm: leading dimension smaller than K");
   int bn = d->block_n > 0 ? d->block_n : choose_block_n(d->N, d->glu);
   if (bn > 256 || (bn % (d->glu ? 64 : 32))) return fail(c, VIMA_E_INVALID, "gemm: bad block_n %d", bn);
@@ -146,13 +182,18 @@ int vima_gemm(vima_ctx* c, const vima_gemm_desc* d, void* stream) {
 
   GemmParams p;
   memset(&p, 0, sizeof(p));
-  const int split = d->a_lo != nullptr;
+  const int split = f8 ? 2 : (d->a_lo != nullptr ? 1 : 0);
   int rc;
   if ((rc = make_tmap(c, &p.tm_a_hi, d->a_hi, d->dtype, d->M, d->K, d->lda, GEMM_BM))) return rc;
   if ((rc = make_tmap(c, &p.tm_b_hi, d->b_hi, d->dtype, d->N, d->K, d->ldb, bn))) return rc;
-  if (split) {
+  if (split == 1) {
     if ((rc = make_tmap(c, &p.tm_a_lo, d->a_lo, d->dtype, d->M, d->K, d->lda, GEMM_BM))) return rc;
     if ((rc = make_tmap(c, &p.tm_b_lo, d->b_lo, d->dtype, d->N, d->K, d->ldb, bn))) return rc;
+  } else if (split == 2) {
+    if ((rc = make_tmap_f8(c, &p.tm_a_lo, d->a_lo8, d->M, d->K, d->lda8, GEMM_BM))) return rc;
+    if ((rc = make_tmap_f8(c, &p.tm_a_hi8, d->a_hi8, d->M, d->K, d->lda8, GEMM_BM))) return rc;
+    if ((rc = make_tmap_f8(c, &p.tm_b_hi8, d->b_hi8, d->N, d->K, d->ldb8, bn))) return rc;
+    if ((rc = make_tmap_f8(c, &p.tm_b_lo, d->b_lo8, d->N, d->K, d->ldb8, bn))) return rc;
   }
   p.M = d->M; p.N = d->N; p.K = d->K;
   p.block_n = bn;
@@ -166,6 +207,7 @@ int vima_gemm(vima_ctx* c, const vima_gemm_desc* d, void* stream) {
   p.residual = d->residual; p.ld_res = d->ld_res;
   p.out_f32 = d->out_f32; p.ld_o32 = d->ld_o32;
   p.out_hi = (unsigned short*)d->out_hi; p.out_lo = (unsigned short*)d->out_lo; p.ld_o16 = d->ld_o16;
+  p.out_lo8 = (unsigned char*)d->out_lo8; p.out_hi8 = (unsigned char*)d->out_hi8; p.ld_o8 = d->ld_o8;
 
   const size_t stage = (size_t)(GEMM_A_TILE_BYTES + bn * 128) * (split ? 2 : 1);
   const size_t fixed = gemm_smem_bytes(bn, split, 0);
@@ -206,6 +248,9 @@ int vima_norm(vima_ctx* c, const vima_norm_desc* d, void* stream) {
   p.out2_f32 = d->out2_f32; p.ld_o2 = d->ld_o2;
   p.out_hi = (unsigned short*)d->out_hi; p.out_lo = (unsigned short*)d->out_lo; p.ld_o16 = d->ld_o16;
   p.dtype = d->dtype;
+  p.out_lo8 = (unsigned char*)d->out_lo8; p.out_hi8 = (unsigned char*)d->out_hi8; p.ld_o8 = d->ld_o8;
+  if ((p.out_lo8 == nullptr) != (p.out_hi8 == nullptr) || (p.out_lo8 && (p.ld_o8 & 3)))
+    return fail(c, VIMA_E_INVALID, "norm: out_lo8/out_hi8 come together with ld_o8 %% 4 == 0");
   LAUNCHED(c, launch_norm(p, (cudaStream_t)stream), "norm");
 }
 
@@ -226,6 +271,9 @@ int vima_attention(vima_ctx* c, const vima_attn_desc* d, void* stream) {
   p.o_hi = (unsigned short*)d->o_hi; p.o_lo = (unsigned short*)d->o_lo; p.ldo = d->ldo;
   p.B = d->B; p.H = d->H; p.Lq = d->Lq; p.Lk = d->Lk; p.D = d->D;
   p.scale = d->scale; p.causal = d->causal; p.split = split; p.dtype = d->dtype;
+  p.o_lo8 = (unsigned char*)d->o_lo8; p.o_hi8 = (unsigned char*)d->o_hi8; p.ldo8 = d->ldo8;
+  if ((p.o_lo8 == nullptr) != (p.o_hi8 == nullptr) || (p.o_lo8 && ((p.ldo8 & 1) || d->dtype != DT_F16)))
+    return fail(c, VIMA_E_INVALID, "attention: o_lo8/o_hi8 come together (fp16 format, even ldo8)");
   LAUNCHED(c, launch_attention(p, (cudaStream_t)stream), "attention");
 }
 

@@ -262,17 +262,24 @@ __global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
     for (int n = 0; n < ND; ++n) {
       const int c = h * D + n * 8 + 2 * t;
       uint32_t hi, lo;
-      if (r0 < Lq) {
-        pack_split<DT>(o[n][0] * inv0, o[n][1] * inv0, hi, lo);
-        const size_t off = (size_t)(b * Lq + r0) * p.ldo + c;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int r = half ? r1 : r0;
+        if (r >= Lq) continue;
+        const float x0 = o[n][2 * half] * (half ? inv1 : inv0), x1 = o[n][2 * half + 1] * (half ? inv1 : inv0);
+        pack_split<DT>(x0, x1, hi, lo);
+        const size_t off = (size_t)(b * Lq + r) * p.ldo + c;
         *reinterpret_cast<uint32_t*>(p.o_hi + off) = hi;
         if (p.o_lo) *reinterpret_cast<uint32_t*>(p.o_lo + off) = lo;
-      }
-      if (r1 < Lq) {
-        pack_split<DT>(o[n][2] * inv1, o[n][3] * inv1, hi, lo);
-        const size_t off = (size_t)(b * Lq + r1) * p.ldo + c;
-        *reinterpret_cast<uint32_t*>(p.o_hi + off) = hi;
-        if (p.o_lo) *reinterpret_cast<uint32_t*>(p.o_lo + off) = lo;
+        if (p.o_lo8) {  // e4m3 cross-term views for an "f16f8" consumer GEMM
+          const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+          unsigned short l8, h8;
+          asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(l8) : "f"((x1 - hf.y) * F8_ACT_LO_SCALE), "f"((x0 - hf.x) * F8_ACT_LO_SCALE));
+          asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(h8) : "f"(x1 * F8_ACT_HI_SCALE), "f"(x0 * F8_ACT_HI_SCALE));
+          const size_t off8 = (size_t)(b * Lq + r) * p.ldo8 + c;
+          *reinterpret_cast<unsigned short*>(p.o_lo8 + off8) = l8;
+          *reinterpret_cast<unsigned short*>(p.o_hi8 + off8) = h8;
+        }
       }
     }
   }

@@ -65,6 +65,29 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_
     asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - hf.y), "f"(x0 - hf.x));
   }
 }
+// ---- fp8 (e4m3) cross-term operands ("f16f8" mode) --------------------------------------------
+// a*b ~= a_hi16*b_hi16 + a_lo8*b_hi8 + a_hi8*b_lo8 with   a_lo8 = e4m3((a - a_hi16) * 2^10),  a_hi8 = e4m3(a * 2^-3),
+//                                                        b_hi8 = e4m3(b * 2^-10),           b_lo8 = e4m3((b - b_hi16) * 2^3)
+// (b already carries the pack-time power-of-two scale), so all three products land in the same accumulator units.
+constexpr float F8_ACT_LO_SCALE = 1024.0f, F8_ACT_HI_SCALE = 0.125f;
+constexpr float F8_W_HI_SCALE = 1.0f / 1024.0f, F8_W_LO_SCALE = 8.0f;
+
+__device__ __forceinline__ uint32_t e4m3x4(float x0, float x1, float x2, float x3) {  // byte 0 = x0
+  unsigned short a, b;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(a) : "f"(x1), "f"(x0));
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(b) : "f"(x3), "f"(x2));
+  return (uint32_t)a | ((uint32_t)b << 16);
+}
+// fp16 hi + the two fp8 views of 4 consecutive values (lo_scale / hi_scale differ for activations and weights)
+__device__ __forceinline__ void split4_f8(const float4& y, float lo_scale, float hi_scale, uint2& hi16, uint32_t& lo8, uint32_t& hi8) {
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi16.x) : "f"(y.y), "f"(y.x));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi16.y) : "f"(y.w), "f"(y.z));
+  const float2 h01 = __half22float2(*reinterpret_cast<const __half2*>(&hi16.x));
+  const float2 h23 = __half22float2(*reinterpret_cast<const __half2*>(&hi16.y));
+  lo8 = e4m3x4((y.x - h01.x) * lo_scale, (y.y - h01.y) * lo_scale, (y.z - h23.x) * lo_scale, (y.w - h23.y) * lo_scale);
+  hi8 = e4m3x4(y.x * hi_scale, y.y * hi_scale, y.z * hi_scale, y.w * hi_scale);
+}
+
 template <int DT>
 __device__ __forceinline__ void split4v(const float4& y, uint2& hi, uint2& lo) {
   split2<DT>(y.x, y.y, hi.x, lo.x);
@@ -185,6 +208,15 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// fp8 (e4m3 x e4m3 -> fp32): same descriptor scheme, K = 32 per instruction.
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }

@@ -27,11 +27,12 @@ constexpr int GEMM_STAGING_BYTES = 4 * 32 * GEMM_ST_LD * 4;  // per-epilogue-war
 constexpr int GEMM_TMEM_COLS = 512;
 
 struct alignas(64) GemmParams {
-  CUtensorMap tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo;
+  CUtensorMap tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo;  // in mode 2: tm_a_lo = A_lo8, tm_b_lo = B_lo8
+  CUtensorMap tm_a_hi8, tm_b_hi8;                    // mode 2 only
   int M, N, K;      // N = accumulator columns (2x the output columns in GLU mode)
   int block_n;      // multiple of 32 (64 in GLU mode), <= 256
   int n_stages;
-  int split;        // 0: hi*hi only, 1: three-term split product
+  int split;        // 0: hi*hi only, 1: three-term fp16 split product, 2: fp16 hi*hi + two fp8 cross terms
   int dtype;        // DT_F16 / DT_BF16 (operand and 16-bit output format)
   int glu;          // 1: out[:, t*bn/2 + c] = act(acc[c]+bias[c]) * (acc[bn/2+c]+bias[bn/2+c]) per tile t
   int act;
@@ -46,6 +47,9 @@ struct alignas(64) GemmParams {
   unsigned short* out_hi; // 16-bit outputs (operand format), or null
   unsigned short* out_lo;
   int ld_o16;
+  unsigned char* out_lo8; // fp8 cross-term views of the output (mode-2 consumers), or null
+  unsigned char* out_hi8;
+  int ld_o8;
 };
 
 // Compile-time epilogue description. GENERIC: every flag is read from GemmParams at run time instead.
@@ -61,6 +65,11 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
   // start address [0,14) (>>4) | LBO [16,30) (ignored for swizzled K-major; 1) | SBO [32,46) = 8 rows * 128 B
   // | version [46,48) = 1 (sm_100) | layout type [61,64) = 2 (SWIZZLE_128B)
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__device__ __forceinline__ uint64_t make_sw64_kmajor_desc(uint32_t smem_addr) {
+  // fp8 tiles: rows of 64 bytes (64 K-elements), SWIZZLE_64B (layout type 4), SBO = 8 rows * 64 B
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
 }
 
 template <int ACT>
@@ -154,6 +163,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_ro
         }
         *reinterpret_cast<uint2*>(p.out_hi + (size_t)row * p.ld_o16 + col) = hi;
         if (p.out_lo) *reinterpret_cast<uint2*>(p.out_lo + (size_t)row * p.ld_o16 + col) = lo;
+        if (p.out_lo8) {  // fp8 cross-term views for a mode-2 consumer (fp16 format only)
+          uint2 h16;
+          uint32_t l8, h8;
+          split4_f8(o, F8_ACT_LO_SCALE, F8_ACT_HI_SCALE, h16, l8, h8);
+          *reinterpret_cast<uint32_t*>(p.out_lo8 + (size_t)row * p.ld_o8 + col) = l8;
+          *reinterpret_cast<uint32_t*>(p.out_hi8 + (size_t)row * p.ld_o8 + col) = h8;
+        }
       }
     }
     __syncwarp();
@@ -167,7 +183,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int BN = p.block_n;
   const int b_tile_bytes = BN * 128;
-  const int n_parts = p.split ? 2 : 1;
+  const int n_parts = p.split ? 2 : 1;  // mode 2: the second "part" holds the two half-size fp8 tiles of each operand
   const int stage_bytes = (GEMM_A_TILE_BYTES + b_tile_bytes) * n_parts;
   uint8_t* stages = smem;
   float* staging = (float*)(smem + (size_t)p.n_stages * stage_bytes);
@@ -193,6 +209,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     if (p.split) {
       tma_prefetch_desc(&p.tm_a_lo);
       tma_prefetch_desc(&p.tm_b_lo);
+    }
+    if (p.split == 2) {
+      tma_prefetch_desc(&p.tm_a_hi8);
+      tma_prefetch_desc(&p.tm_b_hi8);
     }
   }
   if (warp == 1 && lane == 0) {
@@ -228,9 +248,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           tma_load_2d(st, &p.tm_a_hi, &full_bar[stage], k0, m0);
           uint8_t* sb = st + GEMM_A_TILE_BYTES * n_parts;
           tma_load_2d(sb, &p.tm_b_hi, &full_bar[stage], k0, n0);
-          if (p.split) {
+          if (p.split == 1) {
             tma_load_2d(st + GEMM_A_TILE_BYTES, &p.tm_a_lo, &full_bar[stage], k0, m0);
             tma_load_2d(sb + b_tile_bytes, &p.tm_b_lo, &full_bar[stage], k0, n0);
+          } else if (p.split == 2) {  // [A_lo8 | A_hi8] and [B_hi8 | B_lo8]: 64-byte rows, half the fp16 tile each
+            tma_load_2d(st + GEMM_A_TILE_BYTES, &p.tm_a_lo, &full_bar[stage], k0, m0);
+            tma_load_2d(st + GEMM_A_TILE_BYTES + GEMM_A_TILE_BYTES / 2, &p.tm_a_hi8, &full_bar[stage], k0, m0);
+            tma_load_2d(sb + b_tile_bytes, &p.tm_b_hi8, &full_bar[stage], k0, n0);
+            tma_load_2d(sb + b_tile_bytes + b_tile_bytes / 2, &p.tm_b_lo, &full_bar[stage], k0, n0);
           }
           if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
         }
@@ -260,13 +285,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k)  // +32 B per K=16 step inside the 128 B swizzle row
             umma_f16(d_tmem, da_hi + 2 * k, db_hi + 2 * k, idesc, (kb | k) != 0);
-          if (p.split) {
+          if (p.split == 1) {
             const uint64_t da_lo = make_sw128_kmajor_desc(a_hi + GEMM_A_TILE_BYTES);
             const uint64_t db_lo = make_sw128_kmajor_desc(b_hi + b_tile_bytes);
 #pragma unroll
             for (int k = 0; k < GEMM_BK / 16; ++k) umma_f16(d_tmem, da_lo + 2 * k, db_hi + 2 * k, idesc, 1u);
 #pragma unroll
             for (int k = 0; k < GEMM_BK / 16; ++k) umma_f16(d_tmem, da_hi + 2 * k, db_lo + 2 * k, idesc, 1u);
+          } else if (p.split == 2) {
+            // cross terms at the fp8 rate: A_lo8 * B_hi8 and A_hi8 * B_lo8 (e4m3, K = 32 per instruction)
+            const uint32_t idesc8 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
+            const uint64_t da_lo8 = make_sw64_kmajor_desc(a_hi + GEMM_A_TILE_BYTES);
+            const uint64_t da_hi8 = make_sw64_kmajor_desc(a_hi + GEMM_A_TILE_BYTES + GEMM_A_TILE_BYTES / 2);
+            const uint64_t db_hi8 = make_sw64_kmajor_desc(b_hi + b_tile_bytes);
+            const uint64_t db_lo8 = make_sw64_kmajor_desc(b_hi + b_tile_bytes + b_tile_bytes / 2);
+#pragma unroll
+            for (int k = 0; k < GEMM_BK / 32; ++k) umma_f8(d_tmem, da_lo8 + 2 * k, db_hi8 + 2 * k, idesc8, 1u);
+#pragma unroll
+            for (int k = 0; k < GEMM_BK / 32; ++k) umma_f8(d_tmem, da_hi8 + 2 * k, db_lo8 + 2 * k, idesc8, 1u);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
           if (++stage == p.n_stages) { stage = 0; phase ^= 1; }

@@ -14,6 +14,7 @@ struct NormParams {
   float* out2_f32; int ld_o2;         // output of the second norm (fp32), optional
   unsigned short* out_hi; unsigned short* out_lo; int ld_o16;  // last norm's output as 16-bit operands, optional
   int dtype;
+  unsigned char* out_lo8; unsigned char* out_hi8; int ld_o8;   // e4m3 cross-term views, optional
 };
 cudaError_t launch_norm(const NormParams& p, cudaStream_t stream);
 
@@ -26,6 +27,7 @@ struct AttnParams {
   unsigned short *o_hi, *o_lo; int ldo;        // [B*Lq, ldo]
   int B, H, Lq, Lk, D;
   float scale; int causal; int split; int dtype;
+  unsigned char *o_lo8, *o_hi8; int ldo8;      // e4m3 cross-term views of the output, optional
 };
 cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream);
 
@@ -50,6 +52,9 @@ cudaError_t launch_split(const float* x, long long rows, int cols, int ldx, unsi
                          int pad_cols, float scale, int dtype, cudaStream_t s);
 cudaError_t launch_pack_weight(const float* w, int n, int k, int transposed, int ldw, unsigned short* hi, unsigned short* lo, int ld16,
                                float scale, int dtype, cudaStream_t s);
+cudaError_t launch_pack_weight_f8(const float* w, int n, int k, int transposed, int ldw, unsigned char* hi8, unsigned char* lo8, int ld8,
+                                  float scale, cudaStream_t s);
+cudaError_t launch_split_f8(const float* x, long long rows, int cols, int ldx, unsigned char* lo8, unsigned char* hi8, int ld8, cudaStream_t s);
 cudaError_t launch_assemble_history(const float* obs, const unsigned char* obs_mask, const float* act, int T, int B, int Q, int E,
                                     int La, float* tokens, unsigned char* masks_bl, long long* pos_bl, cudaStream_t s);
 cudaError_t launch_mask_cumsum(const unsigned char* mask, int B, int L, long long* pos, cudaStream_t s);

@@ -61,6 +61,56 @@ cudaError_t launch_pack_weight(const float* w, int n, int k, int transposed, int
   return cudaGetLastError();
 }
 
+// e4m3 cross-term views of a packed weight (see common.cuh "f16f8"): hi8 = e4m3(w*scale*2^-10), lo8 = e4m3((w*scale - f16(w*scale))*2^3)
+__global__ void pack_weight_f8_kernel(const float* __restrict__ w, int n, int k, int transposed, int ldw, unsigned char* __restrict__ hi8,
+                                      unsigned char* __restrict__ lo8, int ld8, float scale) {
+  const long long total = (long long)n * (ld8 / 4);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / (ld8 / 4)), c = (int)(i % (ld8 / 4)) * 4;
+    float v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int cc = c + q;
+      v[q] = (cc < k) ? (transposed ? __ldg(w + (size_t)cc * ldw + r) : __ldg(w + (size_t)r * ldw + cc)) * scale : 0.f;
+    }
+    uint2 h16;
+    uint32_t l8, h8;
+    split4_f8(make_float4(v[0], v[1], v[2], v[3]), F8_W_LO_SCALE, F8_W_HI_SCALE, h16, l8, h8);
+    *reinterpret_cast<uint32_t*>(hi8 + (size_t)r * ld8 + c) = h8;
+    *reinterpret_cast<uint32_t*>(lo8 + (size_t)r * ld8 + c) = l8;
+  }
+}
+cudaError_t launch_pack_weight_f8(const float* w, int n, int k, int transposed, int ldw, unsigned char* hi8, unsigned char* lo8, int ld8,
+                                  float scale, cudaStream_t s) {
+  const long long total = (long long)n * (ld8 / 4);
+  if (total == 0) return cudaSuccess;
+  const int blocks = (int)min((total + 255) / 256, (long long)148 * 16);
+  pack_weight_f8_kernel<<<blocks, 256, 0, s>>>(w, n, k, transposed, ldw, hi8, lo8, ld8, scale);
+  return cudaGetLastError();
+}
+
+__global__ void split_f8_kernel(const float* __restrict__ x, long long rows, int cols4, int ldx, unsigned char* __restrict__ lo8,
+                                unsigned char* __restrict__ hi8, int ld8) {
+  const long long total = rows * cols4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols4;
+    const int c = (int)(i % cols4) * 4;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * ldx + c));
+    uint2 h16;
+    uint32_t l8, h8;
+    split4_f8(v, F8_ACT_LO_SCALE, F8_ACT_HI_SCALE, h16, l8, h8);
+    *reinterpret_cast<uint32_t*>(lo8 + r * ld8 + c) = l8;
+    *reinterpret_cast<uint32_t*>(hi8 + r * ld8 + c) = h8;
+  }
+}
+cudaError_t launch_split_f8(const float* x, long long rows, int cols, int ldx, unsigned char* lo8, unsigned char* hi8, int ld8, cudaStream_t s) {
+  const long long total = rows * (cols / 4);
+  if (total == 0) return cudaSuccess;
+  const int blocks = (int)min((total + 255) / 256, (long long)148 * 16);
+  split_f8_kernel<<<blocks, 256, 0, s>>>(x, rows, cols / 4, ldx, lo8, hi8, ld8);
+  return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // History assembly (vima_policy.py:124-147): token l = t*(Q+1)+q <- obs[t,:,q], l = t*(Q+1)+Q <- action[t];
 // masks default True (action slots), position id = cumsum(mask) - 1 along l.

@@ -105,6 +105,21 @@ __global__ void __launch_bounds__(256) norm_rows_kernel(const NormParams p) {
       }
     }
   }
+  if (p.out_lo8) {
+    uint32_t* l8 = reinterpret_cast<uint32_t*>(p.out_lo8 + row * p.ld_o8);
+    uint32_t* h8 = reinterpret_cast<uint32_t*>(p.out_hi8 + row * p.ld_o8);
+#pragma unroll
+    for (int i = 0; i < NORM_MAX_V4; ++i) {
+      const int c = i * 32 + lane;
+      if (c < nv4) {
+        uint2 h16;
+        uint32_t lo8, hi8;
+        split4_f8(v[i], F8_ACT_LO_SCALE, F8_ACT_HI_SCALE, h16, lo8, hi8);
+        l8[c] = lo8;
+        h8[c] = hi8;
+      }
+    }
+  }
 }
 
 cudaError_t launch_norm(const NormParams& p, cudaStream_t stream) {
