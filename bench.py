@@ -375,7 +375,8 @@ def run_ours(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"f16x3": "f16 hi/lo operand pairs (3-term products, fp32-equivalent), fp32 accumulate/softmax/LN",
                       "bf16x3": "bf16 hi/lo operand pairs (3-term), fp32 accumulate", "f16": "f16 operands, fp32 accumulate",
-                      "bf16": "bf16 operands, fp32 accumulate"}[args.precision],
+                      "bf16": "bf16 operands, fp32 accumulate",
+                      "f16f8": "f16 hi*hi + e4m3 cross terms (decoder GEMMs; 2 tensor pass-equivalents), f16 3-term elsewhere, fp32 accumulate/softmax/LN"}[args.precision],
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: VIMA-{case.model} policy step (full-history re-forward), {B} episodes/GPU, Q={Q} object tokens, "
                                    f"Lp={case.Lp} prompt tokens, T={T}-step history (L={case.L})",
@@ -388,8 +389,8 @@ def run_ours(args):
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
                          "kernel": "gemm_tc_kernel (tcgen05)", "launches_per_step": n_gemm / args.steps, "share_of_step": gemm_ms / ms_total,
                          "peak_source": peak_src,
-                         "note": ("algorithmic FLOPs 2MNK per launch; in *x3 modes every product is issued as 3 tensor-core passes, "
-                                  "so tensor-pipe work is 3x the algorithmic figure"),
+                         "note": ("algorithmic FLOPs 2MNK per launch; in *x3 modes every product is issued as 3 tensor-core passes "
+                                  "(f16f8: 1 fp16 pass + 2 fp8 passes), so tensor-pipe work is 3x (2x) the algorithmic figure"),
                          "step_algorithmic_tflop": step_flops / 1e12, "step_tflops": step_flops / (ms_step / 1e3) / 1e12},
         }
         if not args.no_cpu_baseline and world == 1:

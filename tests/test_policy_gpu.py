@@ -52,6 +52,21 @@ def test_policy_matches_reference_golden(name):
     print(name, {k: f"{v:.1e}" for k, v in errs.items()})
 
 
+@pytest.mark.parametrize("name", ["cfg2_small", "cfg3_small"])
+def test_f16f8_mode_within_north_star_tolerance(name):
+    """fp16 hi*hi + e4m3 cross terms for the decoder GEMMs (2 tensor pass-equivalents instead of 3) stays inside 1e-3."""
+    import vima_b200
+
+    case = synth.CASES[name]
+    pol = build_policy(case.model)
+    vima_b200.set_precision("f16f8")
+    try:
+        errs = check_against_golden(name, run_policy_case(pol, case), TOL)
+    finally:
+        vima_b200.set_precision("f16x3")
+    print("f16f8", name, {k: f"{v:.1e}" for k, v in errs.items()})
+
+
 @pytest.mark.parametrize("mode,tol", [("bf16x3", 2e-3), ("f16", 6e-2), ("bf16", 0.5)])
 def test_other_precision_modes(mode, tol):
     """bf16x3 stays near the fp32 bar; the single-pass modes are TF32/bf16-class and only reported."""

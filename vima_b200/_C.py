@@ -32,6 +32,9 @@ class GemmDesc(C.Structure):
         ("out_f32", c_void_p), ("ld_o32", c_int),
         ("out_hi", c_void_p), ("out_lo", c_void_p), ("ld_o16", c_int),
         ("block_n", c_int),
+        ("a_lo8", c_void_p), ("a_hi8", c_void_p), ("lda8", c_int),
+        ("b_hi8", c_void_p), ("b_lo8", c_void_p), ("ldb8", c_int),
+        ("out_lo8", c_void_p), ("out_hi8", c_void_p), ("ld_o8", c_int),
     ]
 
 
@@ -55,6 +58,7 @@ class NormDesc(C.Structure):
         ("out2_f32", c_void_p), ("ld_o2", c_int),
         ("out_hi", c_void_p), ("out_lo", c_void_p), ("ld_o16", c_int),
         ("dtype", c_int),
+        ("out_lo8", c_void_p), ("out_hi8", c_void_p), ("ld_o8", c_int),
     ]
 
 
@@ -67,6 +71,7 @@ class AttnDesc(C.Structure):
         ("o_hi", c_void_p), ("o_lo", c_void_p), ("ldo", c_int),
         ("B", c_int), ("H", c_int), ("Lq", c_int), ("Lk", c_int), ("D", c_int),
         ("scale", c_float), ("causal", c_int), ("dtype", c_int),
+        ("o_lo8", c_void_p), ("o_hi8", c_void_p), ("ldo8", c_int),
     ]
 
 
@@ -77,7 +82,7 @@ EXPORTS = [
     "vima_split_f32", "vima_pack_weight", "vima_gemm", "vima_glu_block_n", "vima_gemm_f32_grouped", "vima_norm",
     "vima_attention", "vima_small_attention", "vima_assemble_history", "vima_mask_cumsum", "vima_add_pos_embed",
     "vima_gather_prompt", "vima_patchify", "vima_vit_tokens", "vima_bbox_norm", "vima_fill_ee", "vima_max_u8",
-    "vima_action_scale", "vima_head_select", "vima_gato_positions",
+    "vima_action_scale", "vima_head_select", "vima_gato_positions", "vima_pack_weight_f8", "vima_split_f8",
 ]
 
 
@@ -162,12 +167,22 @@ class Context:
         self._ck(self.lib.vima_pack_weight(self.h, c_void_p(w.data_ptr()), n, k, int(transposed), w.stride(0), c_void_p(hi.data_ptr()),
                                            c_void_p(_ptr(lo)), hi.stride(0), c_float(scale), dtype, c_void_p(_stream())), "pack_weight")
 
+    def pack_weight_f8(self, w: torch.Tensor, hi8: torch.Tensor, lo8: torch.Tensor, *, transposed: bool, scale=1.0):
+        n, k = (w.shape[1], w.shape[0]) if transposed else (w.shape[0], w.shape[1])
+        self._ck(self.lib.vima_pack_weight_f8(self.h, c_void_p(w.data_ptr()), n, k, int(transposed), w.stride(0), c_void_p(hi8.data_ptr()),
+                                              c_void_p(lo8.data_ptr()), hi8.stride(0), c_float(scale), c_void_p(_stream())), "pack_weight_f8")
+
+    def split_f8(self, x: torch.Tensor, lo8: torch.Tensor, hi8: torch.Tensor):
+        self._ck(self.lib.vima_split_f8(self.h, c_void_p(x.data_ptr()), c_i64(x.shape[0]), x.shape[1], x.stride(0), c_void_p(lo8.data_ptr()),
+                                        c_void_p(hi8.data_ptr()), lo8.stride(0), c_void_p(_stream())), "split_f8")
+
     def glu_block_n(self, n_out: int) -> int:
         return int(self.lib.vima_glu_block_n(int(n_out)))
 
     # ---------------------------------------------------------------- GEMMs
     def gemm(self, *, M, N, K, a_hi, a_lo, lda, b_hi, b_lo, ldb, dtype=DT_F16, glu=0, act=ACT_NONE, acc_scale=1.0, bias=None,
-             mul=None, residual=None, out_f32=None, out_hi=None, out_lo=None, ld_o16=0, block_n=0):
+             mul=None, residual=None, out_f32=None, out_hi=None, out_lo=None, ld_o16=0, block_n=0, a_lo8=None, a_hi8=None, b_hi8=None,
+             b_lo8=None, out_lo8=None, out_hi8=None):
         d = GemmDesc()
         d.M, d.N, d.K = int(M), int(N), int(K)
         d.a_hi, d.a_lo, d.lda = a_hi.data_ptr(), _ptr(a_lo), int(lda)
@@ -179,6 +194,9 @@ class Context:
         d.out_f32, d.ld_o32 = _ptr(out_f32), (out_f32.stride(0) if out_f32 is not None else 0)
         d.out_hi, d.out_lo, d.ld_o16 = _ptr(out_hi), _ptr(out_lo), int(ld_o16 or (out_hi.stride(0) if out_hi is not None else 0))
         d.block_n = int(block_n)
+        d.a_lo8, d.a_hi8, d.lda8 = _ptr(a_lo8), _ptr(a_hi8), (a_lo8.stride(0) if a_lo8 is not None else 0)
+        d.b_hi8, d.b_lo8, d.ldb8 = _ptr(b_hi8), _ptr(b_lo8), (b_hi8.stride(0) if b_hi8 is not None else 0)
+        d.out_lo8, d.out_hi8, d.ld_o8 = _ptr(out_lo8), _ptr(out_hi8), (out_lo8.stride(0) if out_lo8 is not None else 0)
         self._ck(self.lib.vima_gemm(self.h, C.byref(d), c_void_p(_stream())), "gemm")
 
     def gemm_f32_grouped(self, groups_dev: torch.Tensor, n_groups: int, M: int, max_n: int, act: int):
@@ -187,7 +205,7 @@ class Context:
 
     # ---------------------------------------------------------------- norm / attention
     def norm(self, x, *, rows, cols, ldx, w=None, b=None, eps=1e-5, rms=0, add=None, w2=None, b2=None, eps2=1e-5, out_f32=None,
-             out2_f32=None, out_hi=None, out_lo=None, dtype=DT_F16):
+             out2_f32=None, out_hi=None, out_lo=None, dtype=DT_F16, out_lo8=None, out_hi8=None):
         d = NormDesc()
         d.x, d.rows, d.cols, d.ldx = x.data_ptr(), int(rows), int(cols), int(ldx)
         d.add, d.ld_add = _ptr(add), (add.stride(0) if add is not None else 0)
@@ -197,9 +215,10 @@ class Context:
         d.out2_f32, d.ld_o2 = _ptr(out2_f32), (out2_f32.stride(0) if out2_f32 is not None else 0)
         d.out_hi, d.out_lo, d.ld_o16 = _ptr(out_hi), _ptr(out_lo), (out_hi.stride(0) if out_hi is not None else 0)
         d.dtype = dtype
+        d.out_lo8, d.out_hi8, d.ld_o8 = _ptr(out_lo8), _ptr(out_hi8), (out_lo8.stride(0) if out_lo8 is not None else 0)
         self._ck(self.lib.vima_norm(self.h, C.byref(d), c_void_p(_stream())), "norm")
 
-    def attention(self, *, q, k, v, o, B, H, Lq, Lk, D, scale, causal=False, key_mask=None, rel_bias=None, dtype=DT_F16):
+    def attention(self, *, q, k, v, o, B, H, Lq, Lk, D, scale, causal=False, key_mask=None, rel_bias=None, dtype=DT_F16, o8=None):
         """q, k, v, o: (hi, lo|None, ld, column offset) tuples over 16-bit operand buffers."""
         es = 2
 
@@ -214,6 +233,8 @@ class Context:
         d.key_mask, d.rel_bias = _ptr(key_mask), _ptr(rel_bias)
         d.B, d.H, d.Lq, d.Lk, d.D = int(B), int(H), int(Lq), int(Lk), int(D)
         d.scale, d.causal, d.dtype = float(scale), int(causal), dtype
+        if o8 is not None:  # (lo8, hi8) uint8 [rows, ld8]
+            d.o_lo8, d.o_hi8, d.ldo8 = o8[0].data_ptr(), o8[1].data_ptr(), o8[0].stride(0)
         self._ck(self.lib.vima_attention(self.h, C.byref(d), c_void_p(_stream())), "attention")
 
     def small_attention(self, qkv, *, N, S, H, W, scale, o_hi, o_lo, o_f32=None, dtype=DT_F16):

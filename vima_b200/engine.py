@@ -6,6 +6,8 @@ Precision modes (DESIGN.md "operand precision"):
     "bf16x3" same with bf16 pairs (fp32 dynamic range, ~16-bit significand)
     "f16"    single-pass fp16 operands (11-bit significand, TF32-class accuracy)
     "bf16"   single-pass bf16 operands (BASELINE.json configs[1])
+    "f16f8"  fp16 hi*hi plus the two cross terms in e4m3 at the fp8 tensor rate for the decoder GEMMs (2 pass-equivalents
+             instead of 3; ~4e-4 end to end); attention, ViT and T5 stay on the three-term fp16 products
 Accumulation, softmax, LayerNorm, residuals and biases are fp32 in every mode.
 """
 from __future__ import annotations
@@ -18,7 +20,8 @@ import torch
 
 from . import _C
 
-_MODES = {"f16x3": (_C.DT_F16, True), "bf16x3": (_C.DT_BF16, True), "f16": (_C.DT_F16, False), "bf16": (_C.DT_BF16, False)}
+_MODES = {"f16x3": (_C.DT_F16, True), "bf16x3": (_C.DT_BF16, True), "f16": (_C.DT_F16, False), "bf16": (_C.DT_BF16, False),
+          "f16f8": (_C.DT_F16, True)}
 _precision = "f16x3"
 
 
@@ -38,11 +41,12 @@ class Prec:
     name: str
     dtype: int
     split: bool
+    f8: bool = False  # decoder GEMM operands carry e4m3 cross-term views instead of a 16-bit lo part
 
 
 def prec() -> Prec:
     dt, sp = _MODES[_precision]
-    return Prec(_precision, dt, sp)
+    return Prec(_precision, dt, sp, _precision == "f16f8")
 
 
 def ctx_for(t: torch.Tensor) -> _C.Context:
@@ -60,14 +64,20 @@ def round_up(x: int, m: int) -> int:
 class Opnd:
     """A [rows, cols] activation as 16-bit GEMM operand(s): hi (and lo in split mode), leading dim `ld` (mult. of 8)."""
 
-    __slots__ = ("hi", "lo", "rows", "cols", "ld")
+    __slots__ = ("hi", "lo", "rows", "cols", "ld", "lo8", "hi8")
 
-    def __init__(self, rows: int, cols: int, device, split: bool, ld: Optional[int] = None, zero: bool = False):
+    def __init__(self, rows: int, cols: int, device, split: bool, ld: Optional[int] = None, zero: bool = False, f8: bool = False):
+        """split: 16-bit lo part; f8: e4m3 cross-term views (lo8, hi8) INSTEAD of the 16-bit lo part ("f16f8" GEMM inputs)."""
         self.rows, self.cols = rows, cols
         self.ld = round_up(cols, 8) if ld is None else ld
         mk = torch.zeros if (zero or self.ld != cols) else torch.empty
         self.hi = mk((max(rows, 1), self.ld), dtype=torch.int16, device=device)
-        self.lo = mk((max(rows, 1), self.ld), dtype=torch.int16, device=device) if split else None
+        self.lo = mk((max(rows, 1), self.ld), dtype=torch.int16, device=device) if (split and not f8) else None
+        self.lo8 = self.hi8 = None
+        if f8:
+            ld8 = round_up(cols, 16)
+            self.lo8 = torch.zeros((max(rows, 1), ld8), dtype=torch.uint8, device=device) if ld8 != cols else torch.empty((max(rows, 1), ld8), dtype=torch.uint8, device=device)
+            self.hi8 = torch.zeros_like(self.lo8) if ld8 != cols else torch.empty_like(self.lo8)
 
     def sub(self, r0: int, n_rows: int, c0: int = 0, n_cols: Optional[int] = None) -> "Opnd":
         """A window [r0:r0+n_rows, c0:c0+n_cols] sharing storage (as GEMM input c0 must be a multiple of 8)."""
@@ -75,6 +85,8 @@ class Opnd:
         v.rows, v.cols, v.ld = n_rows, (self.cols - c0 if n_cols is None else n_cols), self.ld
         v.hi = self.hi[r0 : r0 + max(n_rows, 1), c0:]
         v.lo = None if self.lo is None else self.lo[r0 : r0 + max(n_rows, 1), c0:]
+        v.lo8 = None if self.lo8 is None else self.lo8[r0 : r0 + max(n_rows, 1), c0:]
+        v.hi8 = None if self.hi8 is None else self.hi8[r0 : r0 + max(n_rows, 1), c0:]
         return v
 
     def float(self, p: Prec) -> torch.Tensor:
@@ -89,7 +101,7 @@ class Opnd:
 class PackedWeight:
     """K-major 16-bit packed weight [n_rows, ld] (+lo), optional fp32 bias in accumulator-column order."""
 
-    __slots__ = ("hi", "lo", "n", "k", "ld", "inv_scale", "bias", "glu", "block_n", "n_out")
+    __slots__ = ("hi", "lo", "n", "k", "ld", "inv_scale", "bias", "glu", "block_n", "n_out", "hi8", "lo8")
 
 
 def _pow2_scale(w_absmax: float, p: Prec) -> float:
@@ -99,8 +111,8 @@ def _pow2_scale(w_absmax: float, p: Prec) -> float:
     return 2.0 ** math.floor(math.log2(1024.0 / w_absmax))
 
 
-def pack_linear(ctx: _C.Context, weight: torch.Tensor, bias: Optional[torch.Tensor], *, transposed: bool, p: Prec) -> PackedWeight:
-    """nn.Linear weight [n, k] or HF Conv1D weight [k, n] (transposed=True)."""
+def pack_linear(ctx: _C.Context, weight: torch.Tensor, bias: Optional[torch.Tensor], *, transposed: bool, p: Prec, f8: bool = False) -> PackedWeight:
+    """nn.Linear weight [n, k] or HF Conv1D weight [k, n] (transposed=True).  f8: also the e4m3 cross-term views."""
     w = weight.detach()
     if w.dtype != torch.float32:
         w = w.float()
@@ -112,14 +124,21 @@ def pack_linear(ctx: _C.Context, weight: torch.Tensor, bias: Optional[torch.Tens
     pw.inv_scale = 1.0 / scale
     pw.hi = torch.empty((n, pw.ld), dtype=torch.int16, device=w.device)
     pw.lo = torch.empty_like(pw.hi) if p.split else None
+    f8 = f8 and p.f8
+    pw.lo = None if f8 else pw.lo
     ctx.pack_weight(w, pw.hi, pw.lo, transposed=transposed, scale=scale, dtype=p.dtype)
+    pw.hi8 = pw.lo8 = None
+    if f8:
+        pw.hi8 = torch.empty((n, round_up(k, 16)), dtype=torch.uint8, device=w.device)
+        pw.lo8 = torch.empty_like(pw.hi8)
+        ctx.pack_weight_f8(w, pw.hi8, pw.lo8, transposed=transposed, scale=scale)
     pw.bias = None if bias is None else bias.detach().float().contiguous()
     pw.glu, pw.block_n, pw.n_out = 0, 0, n
     return pw
 
 
 def pack_glu(ctx: _C.Context, w_val: torch.Tensor, b_val: Optional[torch.Tensor], w_gate: torch.Tensor, *, val_transposed: bool,
-             gate_transposed: bool, p: Prec) -> PackedWeight:
+             gate_transposed: bool, p: Prec, f8: bool = False) -> PackedWeight:
     """Interleaves value / gate rows per accumulator tile so one GEMM + GLU epilogue yields act(x Wv + b) * (x Wg)."""
     wv = w_val.detach().float()
     wg = w_gate.detach().float()
@@ -140,7 +159,7 @@ def pack_glu(ctx: _C.Context, w_val: torch.Tensor, b_val: Optional[torch.Tensor]
     W[:, 1] = wg_p
     if b_val is not None:
         Bv[:, 0] = torch.nn.functional.pad(b_val.detach().float(), (0, pad)).view(tiles, half)
-    pw = pack_linear(ctx, W.view(tiles * bn, k), Bv.view(tiles * bn), transposed=False, p=p)
+    pw = pack_linear(ctx, W.view(tiles * bn, k), Bv.view(tiles * bn), transposed=False, p=p, f8=f8)
     pw.glu, pw.block_n, pw.n_out = 1, bn, n_out
     return pw
 
@@ -170,8 +189,10 @@ class WeightCache:
 # op wrappers
 # -------------------------------------------------------------------------------------------------------------
 def gemm(ctx: _C.Context, a: Opnd, w: PackedWeight, p: Prec, *, act=_C.ACT_NONE, residual=None, mul=None, out_f32: Optional[torch.Tensor] = None,
-         out16: Optional[Opnd] = None, want_f32=False, want16=False, out16_ld: Optional[int] = None, rows: Optional[int] = None):
-    """out = epilogue(a @ w^T).  Returns (out_f32 | None, out16 | None)."""
+         out16: Optional[Opnd] = None, want_f32=False, want16=False, out16_ld: Optional[int] = None, rows: Optional[int] = None,
+         out_f8: bool = False):
+    """out = epilogue(a @ w^T).  Returns (out_f32 | None, out16 | None).  out_f8: the 16-bit output carries e4m3 cross-term views
+    (it feeds an "f16f8" GEMM) instead of a 16-bit lo part (attention inputs keep the 16-bit pair)."""
     M = a.rows if rows is None else rows
     if a.cols != w.k:
         raise ValueError(f"gemm: operand has {a.cols} columns, weight expects {w.k}")
@@ -179,13 +200,18 @@ def gemm(ctx: _C.Context, a: Opnd, w: PackedWeight, p: Prec, *, act=_C.ACT_NONE,
     if want_f32 and out_f32 is None:
         out_f32 = torch.empty((M, w.n_out), dtype=torch.float32, device=dev)
     if want16 and out16 is None:
-        out16 = Opnd(M, w.n_out, dev, p.split, ld=out16_ld)
+        out16 = Opnd(M, w.n_out, dev, p.split, ld=out16_ld, f8=out_f8 and p.f8)
     if M == 0:
         return out_f32, out16
-    ctx.gemm(M=M, N=w.n, K=w.k, a_hi=a.hi, a_lo=a.lo, lda=a.ld, b_hi=w.hi, b_lo=w.lo, ldb=w.ld, dtype=p.dtype, glu=w.glu, act=act,
-             acc_scale=w.inv_scale, bias=w.bias, mul=mul, residual=residual, out_f32=out_f32,
+    use_f8 = a.lo8 is not None and w.lo8 is not None
+    if not use_f8 and p.split and (a.lo is None or w.lo is None):
+        raise RuntimeError("gemm: operand formats do not match (16-bit lo part missing on one side)")
+    ctx.gemm(M=M, N=w.n, K=w.k, a_hi=a.hi, a_lo=None if use_f8 else a.lo, lda=a.ld, b_hi=w.hi, b_lo=None if use_f8 else w.lo, ldb=w.ld,
+             dtype=p.dtype, glu=w.glu, act=act, acc_scale=w.inv_scale, bias=w.bias, mul=mul, residual=residual, out_f32=out_f32,
              out_hi=None if out16 is None else out16.hi, out_lo=None if out16 is None else out16.lo,
-             ld_o16=0 if out16 is None else out16.ld, block_n=w.block_n)
+             ld_o16=0 if out16 is None else out16.ld, block_n=w.block_n,
+             a_lo8=a.lo8 if use_f8 else None, a_hi8=a.hi8 if use_f8 else None, b_hi8=w.hi8 if use_f8 else None, b_lo8=w.lo8 if use_f8 else None,
+             out_lo8=None if out16 is None else out16.lo8, out_hi8=None if out16 is None else out16.hi8)
     return out_f32, out16
 
 
@@ -204,15 +230,16 @@ def to_operand(ctx: _C.Context, x: torch.Tensor, p: Prec, *, pad_cols: Optional[
 
 
 def norm(ctx: _C.Context, x: torch.Tensor, p: Prec, *, rows: int, cols: int, ldx: Optional[int] = None, w=None, b=None, eps=1e-5, rms=False,
-         add=None, w2=None, b2=None, eps2=1e-5, want_f32=False, want2_f32=False, want16=False, out_f32=None):
+         add=None, w2=None, b2=None, eps2=1e-5, want_f32=False, want2_f32=False, want16=False, out_f32=None, out_f8: bool = False):
     dev = x.device
     ldx = cols if ldx is None else ldx
     o32 = out_f32 if out_f32 is not None else (torch.empty((rows, cols), dtype=torch.float32, device=dev) if want_f32 else None)
     o2 = torch.empty((rows, cols), dtype=torch.float32, device=dev) if want2_f32 else None
-    o16 = Opnd(rows, cols, dev, p.split) if want16 else None
+    o16 = Opnd(rows, cols, dev, p.split, f8=out_f8 and p.f8) if want16 else None
     if rows:
         ctx.norm(x, rows=rows, cols=cols, ldx=ldx, w=w, b=b, eps=eps, rms=int(rms), add=add, w2=w2, b2=b2, eps2=eps2, out_f32=o32,
-                 out2_f32=o2, out_hi=None if o16 is None else o16.hi, out_lo=None if o16 is None else o16.lo, dtype=p.dtype)
+                 out2_f32=o2, out_hi=None if o16 is None else o16.hi, out_lo=None if o16 is None else o16.lo, dtype=p.dtype,
+                 out_lo8=None if o16 is None else o16.lo8, out_hi8=None if o16 is None else o16.hi8)
     return o32, o2, o16
 
 

@@ -54,11 +54,11 @@ class Block(nn.Module):
 
 def pack_block(ctx, blk: "Block", p) -> dict:
     return {
-        "c_attn": eng.pack_linear(ctx, blk.attn.c_attn.weight, blk.attn.c_attn.bias, transposed=True, p=p),
-        "c_proj": eng.pack_linear(ctx, blk.attn.c_proj.weight, blk.attn.c_proj.bias, transposed=True, p=p),
+        "c_attn": eng.pack_linear(ctx, blk.attn.c_attn.weight, blk.attn.c_attn.bias, transposed=True, p=p, f8=True),
+        "c_proj": eng.pack_linear(ctx, blk.attn.c_proj.weight, blk.attn.c_proj.bias, transposed=True, p=p, f8=True),
         "fc_glu": eng.pack_glu(ctx, blk.mlp.c_fc.weight, blk.mlp.c_fc.bias, blk.mlp.gated_layer.weight, val_transposed=True,
-                               gate_transposed=False, p=p),
-        "mlp_proj": eng.pack_linear(ctx, blk.mlp.c_proj.weight, blk.mlp.c_proj.bias, transposed=True, p=p),
+                               gate_transposed=False, p=p, f8=True),
+        "mlp_proj": eng.pack_linear(ctx, blk.mlp.c_proj.weight, blk.mlp.c_proj.bias, transposed=True, p=p, f8=True),
     }
 
 
@@ -67,21 +67,25 @@ def run_block(ctx, p, W, blk: "Block", x32, x16, c16, *, B, L, E, H, omask, chai
     with `chain_ln` the operands are chain_ln(LN2(...)) (next layer's query LayerNorm), with `want16` they are LN2(...) itself."""
     M = B * L
     d = E // H
+    # operand formats: attention inputs keep the 16-bit (hi, lo) pair; everything that only feeds a GEMM carries e4m3
+    # cross-term views in "f16f8" mode (out_f8=True is a no-op in the other modes)
     _, qkv16 = eng.gemm(ctx, x16, W["c_attn"], p, want16=True)
     ctx.attention(q=(qkv16.hi, qkv16.lo, qkv16.ld, 0), k=(qkv16.hi, qkv16.lo, qkv16.ld, E), v=(qkv16.hi, qkv16.lo, qkv16.ld, 2 * E),
-                  o=(c16.hi, c16.lo, c16.ld, 0), B=B, H=H, Lq=L, Lk=L, D=d, scale=1.0 / math.sqrt(d), causal=True, key_mask=omask, dtype=p.dtype)
+                  o=(c16.hi, c16.lo, c16.ld, 0), B=B, H=H, Lq=L, Lk=L, D=d, scale=1.0 / math.sqrt(d), causal=True, key_mask=omask, dtype=p.dtype,
+                  o8=None if c16.lo8 is None else (c16.lo8, c16.hi8))
     s32, _ = eng.gemm(ctx, c16, W["c_proj"], p, residual=x32, want_f32=True)
     n32, _, n16 = eng.norm(ctx, s32, p, rows=M, cols=E, w=blk.ln_1.weight.detach(), b=blk.ln_1.bias.detach(), eps=blk.ln_1.eps, want_f32=True,
-                           want16=True)
-    _, h16 = eng.gemm(ctx, n16, W["fc_glu"], p, act=_C.ACT_GELU, want16=True)
+                           want16=True, out_f8=True)
+    _, h16 = eng.gemm(ctx, n16, W["fc_glu"], p, act=_C.ACT_GELU, want16=True, out_f8=True)
     s32, _ = eng.gemm(ctx, h16, W["mlp_proj"], p, residual=n32, out_f32=s32)
     del h16
     w, b = blk.ln_2.weight.detach(), blk.ln_2.bias.detach()
     if chain_ln is not None:
         y32, _, nxt16 = eng.norm(ctx, s32, p, rows=M, cols=E, w=w, b=b, eps=blk.ln_2.eps, w2=chain_ln.weight.detach(), b2=chain_ln.bias.detach(),
-                                 eps2=chain_ln.eps, want16=True, out_f32=out_f32, want_f32=out_f32 is None)
+                                 eps2=chain_ln.eps, want16=True, out_f32=out_f32, want_f32=out_f32 is None, out_f8=True)
     else:
-        y32, _, nxt16 = eng.norm(ctx, s32, p, rows=M, cols=E, w=w, b=b, eps=blk.ln_2.eps, want16=want16, out_f32=out_f32, want_f32=out_f32 is None)
+        y32, _, nxt16 = eng.norm(ctx, s32, p, rows=M, cols=E, w=w, b=b, eps=blk.ln_2.eps, want16=want16, out_f32=out_f32, want_f32=out_f32 is None,
+                                 out_f8=True)
     return y32, nxt16
 
 
@@ -145,12 +149,12 @@ class XAttnGPT(nn.Module):
             L = []
             for blk, xa in zip(self.h, self.xattns):
                 d = {}
-                d["wq"] = eng.pack_linear(ctx, xa.query.weight, None, transposed=False, p=p)
-                d["wkv"] = eng.pack_linear(ctx, xa.key_value.weight, None, transposed=False, p=p)
-                d["wo"] = eng.pack_linear(ctx, xa.attention_out.weight, None, transposed=False, p=p)
-                d["w1"] = eng.pack_linear(ctx, xa.linear1.weight, None, transposed=False, p=p)
-                d["wg"] = eng.pack_linear(ctx, xa.gated_layer.weight, None, transposed=False, p=p)
-                d["w2"] = eng.pack_linear(ctx, xa.linear2.weight, None, transposed=False, p=p)
+                d["wq"] = eng.pack_linear(ctx, xa.query.weight, None, transposed=False, p=p, f8=True)
+                d["wkv"] = eng.pack_linear(ctx, xa.key_value.weight, None, transposed=False, p=p, f8=True)
+                d["wo"] = eng.pack_linear(ctx, xa.attention_out.weight, None, transposed=False, p=p, f8=True)
+                d["w1"] = eng.pack_linear(ctx, xa.linear1.weight, None, transposed=False, p=p, f8=True)
+                d["wg"] = eng.pack_linear(ctx, xa.gated_layer.weight, None, transposed=False, p=p, f8=True)
+                d["w2"] = eng.pack_linear(ctx, xa.linear2.weight, None, transposed=False, p=p, f8=True)
                 d.update(pack_block(ctx, blk, p))
                 L.append(d)
             return L
@@ -227,9 +231,16 @@ class XAttnGPT(nn.Module):
         # x = tokens + positions_embed[ids] (fp32 residual stream); kv = prompt + xattn_positions_embed[ids] (operands only)
         x32 = torch.empty((M, E), dtype=torch.float32, device=dev)
         ctx.add_pos_embed(tok, sb, sl, oa_ids, self.positions_embed.weight.detach(), B, L, E, out_f32=x32, err_flag=err)
-        kv16 = eng.Opnd(Mp, E, dev, p.split)
-        ctx.add_pos_embed(ptk, psb, psl, pr_ids, self.xattn_positions_embed.weight.detach(), B, Lp, E, hi=kv16.hi, lo=kv16.lo,
-                          dtype=p.dtype, err_flag=err)
+        kv16 = eng.Opnd(Mp, E, dev, p.split, f8=p.f8)
+        if p.f8:  # prompt + position embedding feeds only the key_value GEMM: fp32 once, then hi16 + e4m3 views
+            kv32 = torch.empty((Mp, E), dtype=torch.float32, device=dev)
+            ctx.add_pos_embed(ptk, psb, psl, pr_ids, self.xattn_positions_embed.weight.detach(), B, Lp, E, out_f32=kv32, hi=kv16.hi, lo=None,
+                              dtype=p.dtype, err_flag=err)
+            ctx.split_f8(kv32, kv16.lo8, kv16.hi8)
+            del kv32
+        else:
+            ctx.add_pos_embed(ptk, psb, psl, pr_ids, self.xattn_positions_embed.weight.detach(), B, Lp, E, hi=kv16.hi, lo=kv16.lo,
+                              dtype=p.dtype, err_flag=err)
         if not self._input_checked:
             if int(err.item()) != 0:
                 raise IndexError("index out of range in self (position id outside the embedding table)")
@@ -239,22 +250,22 @@ class XAttnGPT(nn.Module):
         lnw = lambda ln: (ln.weight.detach(), ln.bias.detach())
         # first layer's query LayerNorm; later ones are chained onto the previous block's LN2
         w, b = lnw(self.xattns[0].layernorm)
-        _, _, qin16 = eng.norm(ctx, x32, p, rows=M, cols=E, w=w, b=b, eps=self.xattns[0].layernorm.eps, want16=True)
+        _, _, qin16 = eng.norm(ctx, x32, p, rows=M, cols=E, w=w, b=b, eps=self.xattns[0].layernorm.eps, want16=True, out_f8=True)
         for i, (blk, xa, W) in enumerate(zip(self.h, self.xattns, layers)):
             # ---------------- XAttention ----------------
             _, q16 = eng.gemm(ctx, qin16, W["wq"], p, want16=True)
             _, kvp16 = eng.gemm(ctx, kv16, W["wkv"], p, want16=True)
-            c16 = eng.Opnd(M, E, dev, p.split)
+            c16 = eng.Opnd(M, E, dev, p.split, f8=p.f8)
             ctx.attention(q=(q16.hi, q16.lo, q16.ld, 0), k=(kvp16.hi, kvp16.lo, kvp16.ld, 0), v=(kvp16.hi, kvp16.lo, kvp16.ld, E),
                           o=(c16.hi, c16.lo, c16.ld, 0), B=B, H=Hx, Lq=L, Lk=Lp, D=d_x, scale=1.0 / math.sqrt(d_x), causal=False,
-                          key_mask=pmask, dtype=p.dtype)
-            a32, a16 = eng.gemm(ctx, c16, W["wo"], p, residual=x32, want_f32=True, want16=True)
+                          key_mask=pmask, dtype=p.dtype, o8=None if c16.lo8 is None else (c16.lo8, c16.hi8))
+            a32, a16 = eng.gemm(ctx, c16, W["wo"], p, residual=x32, want_f32=True, want16=True, out_f8=True)
             w, b = lnw(xa.ln)
-            _, _, n16 = eng.norm(ctx, a32, p, rows=M, cols=E, w=w, b=b, eps=xa.ln.eps, want16=True)
+            _, _, n16 = eng.norm(ctx, a32, p, rows=M, cols=E, w=w, b=b, eps=xa.ln.eps, want16=True, out_f8=True)
             g32, _ = eng.gemm(ctx, a16, W["wg"], p, want_f32=True)
-            _, h16 = eng.gemm(ctx, n16, W["w1"], p, act=_C.ACT_GELU, mul=g32, want16=True)
+            _, h16 = eng.gemm(ctx, n16, W["w1"], p, act=_C.ACT_GELU, mul=g32, want16=True, out_f8=True)
             del g32
-            xb32, xb16 = eng.gemm(ctx, h16, W["w2"], p, residual=a32, want_f32=True, want16=True)
+            xb32, xb16 = eng.gemm(ctx, h16, W["w2"], p, residual=a32, want_f32=True, want16=True, out_f8=True)
             del h16, a32, a16
             # ---------------- causal Block ----------------
             nxt = self.xattns[i + 1].layernorm if i + 1 < self.n_layer else None
@@ -324,10 +335,12 @@ class HFGPT(nn.Module):
             omask = eng.as_u8(custom_mask != 0)
         M, H = B * L, self.n_head
         x32 = torch.empty((M, E), dtype=torch.float32, device=dev)
-        x16 = eng.Opnd(M, E, dev, p.split)
+        x16 = eng.Opnd(M, E, dev, p.split, f8=p.f8)
         ctx.add_pos_embed(xf, sb, sl, ids, self.lm.positions_embed.weight.detach(), B, L, E, out_f32=x32, hi=x16.hi, lo=x16.lo, dtype=p.dtype)
+        if p.f8:
+            ctx.split_f8(x32, x16.lo8, x16.hi8)
         layers = self._wc.get("blocks", tuple(self.lm.h.parameters()), lambda: [pack_block(ctx, blk, p) for blk in self.lm.h])
-        c16 = eng.Opnd(M, E, dev, p.split)
+        c16 = eng.Opnd(M, E, dev, p.split, f8=p.f8)
         for i, (blk, W) in enumerate(zip(self.lm.h, layers)):
             x32, x16 = run_block(ctx, p, W, blk, x32, x16, c16, B=B, L=L, E=E, H=H, omask=omask, want16=i + 1 < self.n_layer)
         out = x32.view(B, L, E)
