@@ -67,7 +67,31 @@ def test_gemm_plain(ctx, dtname, split, M, N, K):
     assert rel(out, ref) < tol, rel(out, ref)
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (1000, 768, 768), (515, 2304, 768), (300, 768, 3072)])
+@pytest.mark.parametrize("split", [False, True])
+@pytest.mark.parametrize("M,N,K", [(4736, 2304, 768), (4741, 768, 3072), (20000, 768, 768)])
+def test_gemm_cluster_multicast(ctx, split, M, N, K):
+    """Shapes big enough for the 2-CTA cluster path (B tile TMA-multicast to both CTAs), incl. an odd number of m-blocks
+    (ghost tile in the last pair) and a ragged last block; the single-CTA path (VIMA_B200_NO_MCAST) must give the same bits."""
+    dt, tdt = DT["f16"]
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g)
+    a_hi, a_lo, lda = split_ops(ctx, A, dt, split)
+    b_hi, b_lo, ldb = split_ops(ctx, W * 256.0, dt, split)
+    out = torch.full((M, N), float("nan"), device="cuda")
+    ctx.gemm(M=M, N=N, K=K, a_hi=a_hi, a_lo=a_lo, lda=lda, b_hi=b_hi, b_lo=b_lo, ldb=ldb, dtype=dt, bias=bias, residual=res, out_f32=out,
+             acc_scale=1 / 256.0)
+    torch.cuda.synchronize()
+    Ar = A if split else merge(a_hi, None, tdt, K)
+    Wr = W if split else merge(b_hi, None, tdt, K) / 256.0
+    ref = Ar.double() @ Wr.double().t() + bias.double() + res.double()
+    assert torch.isfinite(out).all()
+    assert rel(out, ref) < 1e-5, rel(out, ref)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (1000, 768, 768), (515, 2304, 768), (300, 768, 3072), (9472, 2304, 768)])
 def test_gemm_f16f8(ctx, M, N, K):
     """fp16 hi*hi + two e4m3 cross terms: per-GEMM error ~1e-5 (vs 3e-4 for single-pass fp16); also checks the e4m3 views the
     epilogue emits for the next GEMM."""

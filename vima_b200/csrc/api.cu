@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 #include "../../include/vima_b200.h"
 #include "gemm_tc_variants.cuh"
@@ -184,19 +185,25 @@ int vima_gemm(vima_ctx* c, const vima_gemm_desc* d, void* stream) {
   memset(&p, 0, sizeof(p));
   const int split = f8 ? 2 : (d->a_lo != nullptr ? 1 : 0);
   int rc;
+  // 2-CTA clusters with a multicast B tile once there is enough work to keep every SM pair busy; VIMA_B200_NO_MCAST=1 disables
+  const int tiles_m_ = (d->M + GEMM_BM - 1) / GEMM_BM, tiles_n_ = (d->N + bn - 1) / bn;
+  static const bool no_mcast = getenv("VIMA_B200_NO_MCAST") != nullptr;
+  const int mcast = (!no_mcast && (bn % 64) == 0 && ((tiles_m_ + 1) / 2) * tiles_n_ >= c->sm_count / 2 && tiles_m_ >= 2) ? 1 : 0;
+  const int b_box = mcast ? bn / 2 : bn;
   if ((rc = make_tmap(c, &p.tm_a_hi, d->a_hi, d->dtype, d->M, d->K, d->lda, GEMM_BM))) return rc;
-  if ((rc = make_tmap(c, &p.tm_b_hi, d->b_hi, d->dtype, d->N, d->K, d->ldb, bn))) return rc;
+  if ((rc = make_tmap(c, &p.tm_b_hi, d->b_hi, d->dtype, d->N, d->K, d->ldb, b_box))) return rc;
   if (split == 1) {
     if ((rc = make_tmap(c, &p.tm_a_lo, d->a_lo, d->dtype, d->M, d->K, d->lda, GEMM_BM))) return rc;
-    if ((rc = make_tmap(c, &p.tm_b_lo, d->b_lo, d->dtype, d->N, d->K, d->ldb, bn))) return rc;
+    if ((rc = make_tmap(c, &p.tm_b_lo, d->b_lo, d->dtype, d->N, d->K, d->ldb, b_box))) return rc;
   } else if (split == 2) {
     if ((rc = make_tmap_f8(c, &p.tm_a_lo, d->a_lo8, d->M, d->K, d->lda8, GEMM_BM))) return rc;
     if ((rc = make_tmap_f8(c, &p.tm_a_hi8, d->a_hi8, d->M, d->K, d->lda8, GEMM_BM))) return rc;
-    if ((rc = make_tmap_f8(c, &p.tm_b_hi8, d->b_hi8, d->N, d->K, d->ldb8, bn))) return rc;
-    if ((rc = make_tmap_f8(c, &p.tm_b_lo, d->b_lo8, d->N, d->K, d->ldb8, bn))) return rc;
+    if ((rc = make_tmap_f8(c, &p.tm_b_hi8, d->b_hi8, d->N, d->K, d->ldb8, b_box))) return rc;
+    if ((rc = make_tmap_f8(c, &p.tm_b_lo, d->b_lo8, d->N, d->K, d->ldb8, b_box))) return rc;
   }
   p.M = d->M; p.N = d->N; p.K = d->K;
   p.block_n = bn;
+  p.mcast = mcast;
   p.split = split;
   p.dtype = d->dtype;
   p.glu = d->glu;
@@ -216,8 +223,9 @@ int vima_gemm(vima_ctx* c, const vima_gemm_desc* d, void* stream) {
   if (n_stages < 2) return fail(c, VIMA_E_UNSUPPORTED, "gemm: not enough shared memory for 2 stages");
   p.n_stages = n_stages;
   const size_t smem = gemm_smem_bytes(bn, split, n_stages);
-  const int tiles = ((d->M + GEMM_BM - 1) / GEMM_BM) * ((d->N + bn - 1) / bn);
-  const int grid = tiles < c->sm_count ? tiles : c->sm_count;
+  const int tiles = mcast ? ((tiles_m_ + 1) / 2) * tiles_n_ : tiles_m_ * tiles_n_;  // work units
+  int grid = tiles < c->sm_count ? tiles : c->sm_count;
+  if (mcast) grid = 2 * (tiles < c->sm_count / 2 ? tiles : c->sm_count / 2);
   GemmLaunch l;
   l.act = d->act; l.glu = d->glu != 0; l.mul = d->mul != nullptr; l.res = d->residual != nullptr;
   l.o32 = d->out_f32 != nullptr; l.o16 = d->out_hi != nullptr; l.dtype = d->dtype;

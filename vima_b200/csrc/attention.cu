@@ -44,7 +44,7 @@ constexpr float CAUSAL_L2 = -1e4f * LOG2E;
 constexpr float EXIT_L2 = -9000.f * LOG2E;
 
 template <int D, int DT, bool SPLIT>
-__global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(256, (D == 32) ? 2 : 1) attention_kernel(const AttnParams p) {
   constexpr int KS = D / 16;   // k-steps over head_dim for Q K^T
   constexpr int ND = D / 8;    // n-tiles over head_dim for P V
   constexpr int KROW = D + 8;  // padded smem row (halfs) -> conflict-free ldmatrix
@@ -142,21 +142,30 @@ __global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
     for (int kt = 0; kt < n_kt; ++kt) {
       float s[8][4];
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-        const int key = kt * 64 + nt * 8 + lm_row;
+      for (int nt = 0; nt < 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      // MMAs are issued round-robin over 4 independent accumulators so that back-to-back HMMAs never depend on each
+      // other (a chain of 6 dependent HMMAs per accumulator left the pipe 60 % idle: profiles/r1_summary.md section 3)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
 #pragma unroll
         for (int kk = 0; kk < KS; kk += 2) {  // one ldmatrix.x4 = B fragments of two k-steps (32 head-dim columns)
-          uint32_t bh[4], bl[4];
-          ldmatrix_x4(bh, Ks_hi + key * KROW + kk * 16 + lm_chunk);
-          mma16816<DT>(s[nt], qh[kk], bh[0], bh[1]);
-          mma16816<DT>(s[nt], qh[kk + 1], bh[2], bh[3]);
-          if (SPLIT) {
-            mma16816<DT>(s[nt], ql[kk], bh[0], bh[1]);
-            mma16816<DT>(s[nt], ql[kk + 1], bh[2], bh[3]);
-            ldmatrix_x4(bl, Ks_lo + key * KROW + kk * 16 + lm_chunk);
-            mma16816<DT>(s[nt], qh[kk], bl[0], bl[1]);
-            mma16816<DT>(s[nt], qh[kk + 1], bl[2], bl[3]);
+          uint32_t bh[4][4], bl[4][4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int key = kt * 64 + (half * 4 + q) * 8 + lm_row;
+            ldmatrix_x4(bh[q], Ks_hi + key * KROW + kk * 16 + lm_chunk);
+            if (SPLIT) ldmatrix_x4(bl[q], Ks_lo + key * KROW + kk * 16 + lm_chunk);
+          }
+#pragma unroll
+          for (int k2 = 0; k2 < 2; ++k2) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) mma16816<DT>(s[half * 4 + q], qh[kk + k2], bh[q][2 * k2], bh[q][2 * k2 + 1]);
+            if (SPLIT) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) mma16816<DT>(s[half * 4 + q], ql[kk + k2], bh[q][2 * k2], bh[q][2 * k2 + 1]);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) mma16816<DT>(s[half * 4 + q], qh[kk + k2], bl[q][2 * k2], bl[q][2 * k2 + 1]);
+            }
           }
         }
       }
@@ -227,20 +236,26 @@ __global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
         pack_split<DT>(s[2 * k2 + 1][2], s[2 * k2 + 1][3], ph[k2][3], pl[k2][3]);
       }
 #pragma unroll
-      for (int n = 0; n < ND; ++n) {
-        const int drow = n * 8 + lm_row;
+      for (int ng = 0; ng < ND; ng += 4) {  // 4 independent output accumulators per round
 #pragma unroll
         for (int kp = 0; kp < 2; ++kp) {  // one ldmatrix.x4 = V^T fragments of two 16-key steps
-          uint32_t vh4[4], vl4[4];
-          ldmatrix_x4(vh4, Vt_hi + drow * VROW + kt * 64 + kp * 32 + lm_chunk);
-          mma16816<DT>(o[n], ph[2 * kp], vh4[0], vh4[1]);
-          mma16816<DT>(o[n], ph[2 * kp + 1], vh4[2], vh4[3]);
-          if (SPLIT) {
-            mma16816<DT>(o[n], pl[2 * kp], vh4[0], vh4[1]);
-            mma16816<DT>(o[n], pl[2 * kp + 1], vh4[2], vh4[3]);
-            ldmatrix_x4(vl4, Vt_lo + drow * VROW + kt * 64 + kp * 32 + lm_chunk);
-            mma16816<DT>(o[n], ph[2 * kp], vl4[0], vl4[1]);
-            mma16816<DT>(o[n], ph[2 * kp + 1], vl4[2], vl4[3]);
+          uint32_t vh4[4][4], vl4[4][4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int drow = (ng + q) * 8 + lm_row;
+            ldmatrix_x4(vh4[q], Vt_hi + drow * VROW + kt * 64 + kp * 32 + lm_chunk);
+            if (SPLIT) ldmatrix_x4(vl4[q], Vt_lo + drow * VROW + kt * 64 + kp * 32 + lm_chunk);
+          }
+#pragma unroll
+          for (int k2 = 0; k2 < 2; ++k2) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) mma16816<DT>(o[ng + q], ph[2 * kp + k2], vh4[q][2 * k2], vh4[q][2 * k2 + 1]);
+            if (SPLIT) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) mma16816<DT>(o[ng + q], pl[2 * kp + k2], vh4[q][2 * k2], vh4[q][2 * k2 + 1]);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) mma16816<DT>(o[ng + q], ph[2 * kp + k2], vl4[q][2 * k2], vl4[q][2 * k2 + 1]);
+            }
           }
         }
       }

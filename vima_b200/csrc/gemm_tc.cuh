@@ -32,6 +32,7 @@ struct alignas(64) GemmParams {
   int M, N, K;      // N = accumulator columns (2x the output columns in GLU mode)
   int block_n;      // multiple of 32 (64 in GLU mode), <= 256
   int n_stages;
+  int mcast;        // 1: launched as 2-CTA clusters; the pair shares one B tile (each CTA TMA-multicasts half of it)
   int split;        // 0: hi*hi only, 1: three-term fp16 split product, 2: fp16 hi*hi + two fp8 cross terms
   int dtype;        // DT_F16 / DT_BF16 (operand and 16-bit output format)
   int glu;          // 1: out[:, t*bn/2 + c] = act(acc[c]+bias[c]) * (acc[bn/2+c]+bias[bn/2+c]) per tile t
@@ -200,8 +201,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 
   const int tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
   const int tiles_n = (p.N + BN - 1) / BN;
-  const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+  // Work units: single tiles, or (mcast) PAIRS of vertically adjacent tiles (m_blk = 2*pair_m + rank, same n) handled by the
+  // two CTAs of a cluster so that one B tile feeds both.  A CTA whose m-block falls off the end runs a ghost tile (zero-filled
+  // loads, no stores) to keep the pair's barrier protocol in step.
+  const int mc = p.mcast;
+  const uint32_t crank = mc ? cluster_ctarank() : 0u;
+  const int unit0 = mc ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_stride = mc ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int num_tiles = (mc ? (tiles_m + 1) / 2 : tiles_m) * tiles_n;  // number of work units
+  auto unit_m0 = [&](int u) { return ((mc ? 2 * (u / tiles_n) + (int)crank : u / tiles_n)) * GEMM_BM; };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tm_a_hi);
@@ -218,7 +227,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.n_stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], mc ? 2 : 1);  // mcast: both CTAs' MMAs must have drained the slot
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -229,6 +238,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   if (warp == 2) tmem_alloc<GEMM_TMEM_COLS>(tmem_ptr_smem);
   tcgen05_fence_before();
   __syncthreads();
+  if (mc) cluster_sync_all();  // the peer's barriers are initialised before anything can arrive on them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -237,25 +247,32 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / tiles_n) * GEMM_BM;
+      for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
+        const int m0 = unit_m0(tile);
         const int n0 = (tile % tiles_n) * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = stages + (size_t)stage * stage_bytes;
           mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
           const int k0 = kb * GEMM_BK;
-          tma_load_2d(st, &p.tm_a_hi, &full_bar[stage], k0, m0);
           uint8_t* sb = st + GEMM_A_TILE_BYTES * n_parts;
-          tma_load_2d(sb, &p.tm_b_hi, &full_bar[stage], k0, n0);
+          // B: whole tile, or (mcast) this CTA's half of the rows, multicast to both CTAs of the pair
+          const int bh = mc ? BN / 2 : 0;  // rows per half
+          const int brow = n0 + (int)crank * bh;
+          auto load_b = [&](uint8_t* dst_tile, int row_bytes, const CUtensorMap* tm) {
+            if (mc) tma_load_2d_mcast(dst_tile + (size_t)crank * bh * row_bytes, tm, &full_bar[stage], k0, brow, (uint16_t)3);
+            else tma_load_2d(dst_tile, tm, &full_bar[stage], k0, n0);
+          };
+          tma_load_2d(st, &p.tm_a_hi, &full_bar[stage], k0, m0);
+          load_b(sb, 128, &p.tm_b_hi);
           if (p.split == 1) {
             tma_load_2d(st + GEMM_A_TILE_BYTES, &p.tm_a_lo, &full_bar[stage], k0, m0);
-            tma_load_2d(sb + b_tile_bytes, &p.tm_b_lo, &full_bar[stage], k0, n0);
+            load_b(sb + b_tile_bytes, 128, &p.tm_b_lo);
           } else if (p.split == 2) {  // [A_lo8 | A_hi8] and [B_hi8 | B_lo8]: 64-byte rows, half the fp16 tile each
             tma_load_2d(st + GEMM_A_TILE_BYTES, &p.tm_a_lo, &full_bar[stage], k0, m0);
             tma_load_2d(st + GEMM_A_TILE_BYTES + GEMM_A_TILE_BYTES / 2, &p.tm_a_hi8, &full_bar[stage], k0, m0);
-            tma_load_2d(sb + b_tile_bytes, &p.tm_b_hi8, &full_bar[stage], k0, n0);
-            tma_load_2d(sb + b_tile_bytes + b_tile_bytes / 2, &p.tm_b_lo, &full_bar[stage], k0, n0);
+            load_b(sb + b_tile_bytes, 64, &p.tm_b_hi8);
+            load_b(sb + b_tile_bytes + b_tile_bytes / 2, 64, &p.tm_b_lo);
           }
           if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
         }
@@ -271,7 +288,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       uint32_t phase = 0;
       int ab = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
         mbar_wait(&tmem_empty[ab], aphase ^ 1);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(ab * 256);
@@ -304,7 +321,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 #pragma unroll
             for (int k = 0; k < GEMM_BK / 32; ++k) umma_f8(d_tmem, da_hi8 + 2 * k, db_lo8 + 2 * k, idesc8, 1u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          // frees the smem slot when these MMAs retire (in both CTAs of the pair when the slot is multicast-fed)
+          if (mc) umma_commit_mcast(&empty_bar[stage], (uint16_t)3); else umma_commit(&empty_bar[stage]);
           if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full[ab]);  // accumulator complete -> epilogue
@@ -327,7 +345,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     // loads are L2 hits instead of ~1 us DRAM round trips (they cannot be issued deep enough from registers).
     auto prefetch_tile = [&](int t) {
       if (!(has_mul || has_res) || t >= num_tiles) return;
-      const int row = (t / tiles_n) * GEMM_BM + et;
+      const int row = unit_m0(t) + et;
       if (row >= p.M) return;
       const int c0 = (t % tiles_n) * bn_out;
       for (int c = 0; c < bn_out && c0 + c < n_out; c += 32) {
@@ -335,10 +353,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         if (has_res) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.residual + (size_t)row * p.ld_res + c0 + c));
       }
     };
-    prefetch_tile(blockIdx.x);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      prefetch_tile(tile + gridDim.x);
-      const int m0 = (tile / tiles_n) * GEMM_BM;
+    prefetch_tile(unit0);
+    for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
+      prefetch_tile(tile + unit_stride);
+      const int m0 = unit_m0(tile);
       const int tn = tile % tiles_n;
       const int n0 = tn * BN;
       float* sb = sbias + ab * 256;
@@ -358,6 +376,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 
   tcgen05_fence_before();
   __syncthreads();
+  if (mc) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it / arrive on its barriers
   if (warp == 2) {
     tcgen05_fence_after();
     tmem_dealloc<GEMM_TMEM_COLS>(tmem_base);

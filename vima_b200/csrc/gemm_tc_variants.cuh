@@ -33,6 +33,21 @@ inline cudaError_t launch_one(const GemmParams& p, int grid, size_t smem, int ma
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
+  if (p.mcast) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<E>, p);
+  }
   gemm_tc_kernel<E><<<grid, GEMM_THREADS, smem, stream>>>(p);
   return cudaGetLastError();
 }
