@@ -20,10 +20,10 @@ namespace vima {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;                       // 64 x 2 B = 128 B = one swizzle row
 constexpr int GEMM_A_TILE_BYTES = GEMM_BM * 128;  // 16 KB
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;       // 4 control warps (TMA, MMA, TMEM alloc, spare) + 8 epilogue warps
+constexpr int GEMM_EPI_WARPS = 8;       // two per TMEM lane quadrant: each takes every other 32-column chunk
 constexpr int GEMM_MAX_STAGES = 8;
-constexpr int GEMM_ST_LD = 36;                               // padded row of the transpose buffer (floats)
-constexpr int GEMM_STAGING_BYTES = 4 * 32 * GEMM_ST_LD * 4;  // per-epilogue-warp 32x36 fp32 transpose buffers
+constexpr int GEMM_STAGING_BYTES = GEMM_EPI_WARPS * 32 * 16 * 4;  // per-epilogue-warp 32x16 fp32 transpose buffers (XOR-swizzled)
 constexpr int GEMM_TMEM_COLS = 512;
 
 struct alignas(64) GemmParams {
@@ -84,96 +84,107 @@ __device__ __forceinline__ float act_ct(float x) {
 template <int DT>
 __device__ __forceinline__ void split4(const float4& y, uint2& hi, uint2& lo) { split4v<DT>(y, hi, lo); }
 
-// One accumulator tile (this warp's 32 rows): TMEM -> registers (row per thread) -> bias/act/GLU -> smem transpose
-// -> [rows of 4 x 8 lanes x float4] -> mul / residual / stores, all 128-bit and coalesced.
+// One accumulator tile, this warp's share: rows [32*quadrant, +32) x every other 32-column chunk (ehalf selects which).
+// Per 16-column sub-chunk: TMEM -> registers (row per thread) -> bias/act/GLU -> smem transpose (32x16 floats, 16-byte chunks
+// XOR-swizzled by (row>>1)&3: conflict-free both ways) -> [8 rows x 4 lanes x float4] -> mul / residual / stores (128-bit fp32,
+// 64-bit 16-bit pairs), issued after the sub-chunk's global loads are already in flight.
 template <class E>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_row, const float* __restrict__ sb, float* __restrict__ st,
-                                              int lane, int row_base, int tn, int bn_out, int n_out) {
+                                              int lane, int ehalf, int row_base, int tn, int bn_out, int n_out) {
   const bool glu = E::GENERIC ? (p.glu != 0) : E::GLU;
   const bool has_mul = E::GENERIC ? (p.mul != nullptr) : E::MUL;
   const bool has_res = E::GENERIC ? (p.residual != nullptr) : E::RES;
   const bool o32 = E::GENERIC ? (p.out_f32 != nullptr) : E::O32;
   const bool o16 = E::GENERIC ? (p.out_hi != nullptr) : E::O16;
   const float scale = p.acc_scale;
-  const int sub = lane >> 3;        // row within a group of 4
-  const int c4 = (lane & 7) * 4;    // first of this lane's 4 columns inside the 32-column chunk
-  for (int j = 0; j < bn_out; j += 32) {
-    // issue this chunk's multiplier / residual loads first: they fly while the accumulator is read and activated
-    const int col = tn * bn_out + j + c4;
-    const bool col_ok = col < n_out;  // n_out % 4 == 0 (checked on the host)
-    float4 mm[8], rr[8];
+  const int sub = lane >> 2;        // row within a group of 8
+  const int kc = lane & 3;          // which 4-column group of the 16-column sub-chunk
+  for (int j0 = ehalf * 32; j0 < bn_out; j0 += 64) {
+#pragma unroll 1
+    for (int j = j0; j < j0 + 32; j += 16) {
+      const int col = tn * bn_out + j + kc * 4;
+      const bool col_ok = col < n_out;  // n_out % 4 == 0 (checked on the host)
+      float4 mm[4], rr[4];
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int row = row_base + it * 4 + sub;
-      const bool ok = col_ok && row < p.M;
-      if (has_mul) mm[it] = ok ? __ldg(reinterpret_cast<const float4*>(p.mul + (size_t)row * p.ld_mul + col)) : make_float4(1.f, 1.f, 1.f, 1.f);
-      if (has_res) rr[it] = ok ? __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)row * p.ld_res + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    uint32_t v[32];
-    tmem_ld_32x32(t_row + j, v);
-    float x[32];
-    if (glu) {
-      uint32_t g[32];
-      tmem_ld_32x32(t_row + bn_out + j, g);
-      tmem_ld_wait();
+      for (int it = 0; it < 4; ++it) {
+        const int row = row_base + it * 8 + sub;
+        const bool ok = col_ok && row < p.M;
+        if (has_mul) mm[it] = ok ? __ldg(reinterpret_cast<const float4*>(p.mul + (size_t)row * p.ld_mul + col)) : make_float4(1.f, 1.f, 1.f, 1.f);
+        if (has_res) rr[it] = ok ? __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)row * p.ld_res + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      uint32_t v[16];
+      tmem_ld_32x16(t_row + j, v);
+      float x[16];
+      if (glu) {
+        uint32_t g[16];
+        tmem_ld_32x16(t_row + bn_out + j, g);
+        tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        const float4 b1 = *reinterpret_cast<const float4*>(sb + j + i);
-        const float4 b2 = *reinterpret_cast<const float4*>(sb + bn_out + j + i);
-        const float bb1[4] = {b1.x, b1.y, b1.z, b1.w}, bb2[4] = {b2.x, b2.y, b2.z, b2.w};
+        for (int i = 0; i < 16; i += 4) {
+          const float4 b1 = *reinterpret_cast<const float4*>(sb + j + i);
+          const float4 b2 = *reinterpret_cast<const float4*>(sb + bn_out + j + i);
+          const float bb1[4] = {b1.x, b1.y, b1.z, b1.w}, bb2[4] = {b2.x, b2.y, b2.z, b2.w};
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float a = __uint_as_float(v[i + q]) * scale + bb1[q];
-          a = E::GENERIC ? apply_act(p.act, a) : act_ct<E::ACT>(a);
-          x[i + q] = a * (__uint_as_float(g[i + q]) * scale + bb2[q]);
+          for (int q = 0; q < 4; ++q) {
+            float a = fmaf(__uint_as_float(v[i + q]), scale, bb1[q]);
+            a = E::GENERIC ? apply_act(p.act, a) : act_ct<E::ACT>(a);
+            x[i + q] = a * fmaf(__uint_as_float(g[i + q]), scale, bb2[q]);
+          }
+        }
+      } else {
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          const float4 b1 = *reinterpret_cast<const float4*>(sb + j + i);
+          const float bb1[4] = {b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float a = fmaf(__uint_as_float(v[i + q]), scale, bb1[q]);
+            x[i + q] = E::GENERIC ? apply_act(p.act, a) : act_ct<E::ACT>(a);
+          }
         }
       }
-    } else {
-      tmem_ld_wait();
+      const int wsw = (lane >> 1) & 3;  // this thread's row is `lane`
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        const float4 b1 = *reinterpret_cast<const float4*>(sb + j + i);
-        const float bb1[4] = {b1.x, b1.y, b1.z, b1.w};
+      for (int k = 0; k < 4; ++k)
+        *reinterpret_cast<float4*>(st + lane * 16 + ((k ^ wsw) << 2)) = make_float4(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]);
+      __syncwarp();
+      float4 y[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float a = __uint_as_float(v[i + q]) * scale + bb1[q];
-          x[i + q] = E::GENERIC ? apply_act(p.act, a) : act_ct<E::ACT>(a);
+      for (int it = 0; it < 4; ++it) {
+        const int r = it * 8 + sub;
+        y[it] = *reinterpret_cast<const float4*>(st + r * 16 + ((kc ^ ((r >> 1) & 3)) << 2));
+      }
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int row = row_base + it * 8 + sub;
+        if (!(col_ok && row < p.M)) continue;
+        float4 o = y[it];
+        if (has_mul) { o.x *= mm[it].x; o.y *= mm[it].y; o.z *= mm[it].z; o.w *= mm[it].w; }
+        if (has_res) { o.x += rr[it].x; o.y += rr[it].y; o.z += rr[it].z; o.w += rr[it].w; }
+        if (o32) *reinterpret_cast<float4*>(p.out_f32 + (size_t)row * p.ld_o32 + col) = o;
+        if (o16) {
+          if (p.out_lo8) {  // fp16 hi + e4m3 cross-term views for an "f16f8" consumer
+            uint2 h16;
+            uint32_t l8, h8;
+            split4_f8(o, F8_ACT_LO_SCALE, F8_ACT_HI_SCALE, h16, l8, h8);
+            *reinterpret_cast<uint2*>(p.out_hi + (size_t)row * p.ld_o16 + col) = h16;
+            *reinterpret_cast<uint32_t*>(p.out_lo8 + (size_t)row * p.ld_o8 + col) = l8;
+            *reinterpret_cast<uint32_t*>(p.out_hi8 + (size_t)row * p.ld_o8 + col) = h8;
+          } else {
+            uint2 hi, lo;
+            if (E::GENERIC) {
+              if (p.dtype == DT_F16) split4<DT_F16>(o, hi, lo); else split4<DT_BF16>(o, hi, lo);
+            } else {
+              split4<E::DT>(o, hi, lo);
+            }
+            *reinterpret_cast<uint2*>(p.out_hi + (size_t)row * p.ld_o16 + col) = hi;
+            if (p.out_lo) *reinterpret_cast<uint2*>(p.out_lo + (size_t)row * p.ld_o16 + col) = lo;
+          }
         }
       }
+      __syncwarp();
     }
-#pragma unroll
-    for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(st + lane * GEMM_ST_LD + i) = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
-    __syncwarp();
-    float4 y[8];
-#pragma unroll
-    for (int it = 0; it < 8; ++it) y[it] = *reinterpret_cast<const float4*>(st + (it * 4 + sub) * GEMM_ST_LD + c4);
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int row = row_base + it * 4 + sub;
-      if (!(col_ok && row < p.M)) continue;
-      float4 o = y[it];
-      if (has_mul) { o.x *= mm[it].x; o.y *= mm[it].y; o.z *= mm[it].z; o.w *= mm[it].w; }
-      if (has_res) { o.x += rr[it].x; o.y += rr[it].y; o.z += rr[it].z; o.w += rr[it].w; }
-      if (o32) *reinterpret_cast<float4*>(p.out_f32 + (size_t)row * p.ld_o32 + col) = o;
-      if (o16) {
-        uint2 hi, lo;
-        if (E::GENERIC) {
-          if (p.dtype == DT_F16) split4<DT_F16>(o, hi, lo); else split4<DT_BF16>(o, hi, lo);
-        } else {
-          split4<E::DT>(o, hi, lo);
-        }
-        *reinterpret_cast<uint2*>(p.out_hi + (size_t)row * p.ld_o16 + col) = hi;
-        if (p.out_lo) *reinterpret_cast<uint2*>(p.out_lo + (size_t)row * p.ld_o16 + col) = lo;
-        if (p.out_lo8) {  // fp8 cross-term views for a mode-2 consumer (fp16 format only)
-          uint2 h16;
-          uint32_t l8, h8;
-          split4_f8(o, F8_ACT_LO_SCALE, F8_ACT_HI_SCALE, h16, l8, h8);
-          *reinterpret_cast<uint32_t*>(p.out_lo8 + (size_t)row * p.ld_o8 + col) = l8;
-          *reinterpret_cast<uint32_t*>(p.out_hi8 + (size_t)row * p.ld_o8 + col) = h8;
-        }
-      }
-    }
-    __syncwarp();
   }
 }
 
@@ -231,7 +242,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], GEMM_EPI_WARPS);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -331,9 +342,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int we = warp - 4;  // == warp % 4 : TMEM lane quadrant
-    float* st = staging + we * (32 * GEMM_ST_LD);
-    const int et = threadIdx.x - 128;  // 0..127
+    const int we = warp & 3;           // TMEM lane quadrant this warp may read
+    const int ehalf = (warp - 4) >> 2;  // which of the two warps of the quadrant
+    float* st = staging + (warp - 4) * (32 * 16);
+    const int et = threadIdx.x - 128;  // 0..255
     const bool glu = E::GENERIC ? (p.glu != 0) : E::GLU;
     const int n_out = glu ? p.N / 2 : p.N;
     const int bn_out = glu ? BN / 2 : BN;
@@ -345,6 +357,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     // loads are L2 hits instead of ~1 us DRAM round trips (they cannot be issued deep enough from registers).
     auto prefetch_tile = [&](int t) {
       if (!(has_mul || has_res) || t >= num_tiles) return;
+      if (et >= GEMM_BM) return;
       const int row = unit_m0(t) + et;
       if (row >= p.M) return;
       const int c0 = (t % tiles_n) * bn_out;
@@ -361,12 +374,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       const int n0 = tn * BN;
       float* sb = sbias + ab * 256;
       // bias tile -> smem (visible to the 4 epilogue warps after the named barrier)
-      for (int c = et; c < BN; c += 128) sb[c] = (p.bias != nullptr && n0 + c < p.N) ? __ldg(p.bias + n0 + c) : 0.f;
-      named_bar_sync(1, 128);
+      for (int c = et; c < BN; c += 32 * GEMM_EPI_WARPS) sb[c] = (p.bias != nullptr && n0 + c < p.N) ? __ldg(p.bias + n0 + c) : 0.f;
+      named_bar_sync(1, 32 * GEMM_EPI_WARPS);
       mbar_wait(&tmem_full[ab], aphase);
       tcgen05_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(we * 32) << 16) + (uint32_t)(ab * 256);
-      epilogue_tile<E>(p, t_row, sb, st, lane, m0 + we * 32, tn, bn_out, n_out);
+      epilogue_tile<E>(p, t_row, sb, st, lane, ehalf, m0 + we * 32, tn, bn_out, n_out);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[ab]);
