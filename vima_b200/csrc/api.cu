@@ -187,9 +187,13 @@ int vima_gemm(vima_ctx* c, const vima_gemm_desc* d, void* stream) {
   int rc;
   // 2-CTA clusters with a multicast B tile once there is enough work to keep every SM pair busy; VIMA_B200_NO_MCAST=1 disables
   const int tiles_m_ = (d->M + GEMM_BM - 1) / GEMM_BM, tiles_n_ = (d->N + bn - 1) / bn;
-  static const bool no_mcast = getenv("VIMA_B200_NO_MCAST") != nullptr;
-  const int mcast = (!no_mcast && (bn % 64) == 0 && ((tiles_m_ + 1) / 2) * tiles_n_ >= c->sm_count / 2 && tiles_m_ >= 2) ? 1 : 0;
-  const int b_box = mcast ? bn / 2 : bn;
+  // VIMA_B200_GEMM_MODE = 1cta | mcast | 2cta (default 2cta: cta_group::2 pairs, M = 256, each CTA stages half of the B tile)
+  static const char* mode_env = getenv("VIMA_B200_GEMM_MODE");
+  static const int mode_pref = (mode_env && !strcmp(mode_env, "1cta")) ? 0 : (mode_env && !strcmp(mode_env, "mcast")) ? 1 : 2;
+  const bool pair_ok = (bn % 64) == 0 && ((tiles_m_ + 1) / 2) * tiles_n_ >= c->sm_count / 2 && tiles_m_ >= 2;
+  const int mcast = (pair_ok && mode_pref == 1) ? 1 : 0;
+  const int two_cta = (pair_ok && mode_pref == 2) ? 1 : 0;
+  const int b_box = (mcast || two_cta) ? bn / 2 : bn;
   if ((rc = make_tmap(c, &p.tm_a_hi, d->a_hi, d->dtype, d->M, d->K, d->lda, GEMM_BM))) return rc;
   if ((rc = make_tmap(c, &p.tm_b_hi, d->b_hi, d->dtype, d->N, d->K, d->ldb, b_box))) return rc;
   if (split == 1) {
@@ -204,6 +208,7 @@ int vima_gemm(vima_ctx* c, const vima_gemm_desc* d, void* stream) {
   p.M = d->M; p.N = d->N; p.K = d->K;
   p.block_n = bn;
   p.mcast = mcast;
+  p.two_cta = two_cta;
   p.split = split;
   p.dtype = d->dtype;
   p.glu = d->glu;
@@ -216,16 +221,16 @@ int vima_gemm(vima_ctx* c, const vima_gemm_desc* d, void* stream) {
   p.out_hi = (unsigned short*)d->out_hi; p.out_lo = (unsigned short*)d->out_lo; p.ld_o16 = d->ld_o16;
   p.out_lo8 = (unsigned char*)d->out_lo8; p.out_hi8 = (unsigned char*)d->out_hi8; p.ld_o8 = d->ld_o8;
 
-  const size_t stage = (size_t)(GEMM_A_TILE_BYTES + bn * 128) * (split ? 2 : 1);
-  const size_t fixed = gemm_smem_bytes(bn, split, 0);
+  const size_t stage = (size_t)(GEMM_A_TILE_BYTES + (two_cta ? bn / 2 : bn) * 128) * (split ? 2 : 1);
+  const size_t fixed = gemm_smem_bytes(bn, split, 0, two_cta);
   int n_stages = (int)(((size_t)c->max_smem_optin - fixed) / stage);
   if (n_stages > GEMM_MAX_STAGES) n_stages = GEMM_MAX_STAGES;
   if (n_stages < 2) return fail(c, VIMA_E_UNSUPPORTED, "gemm: not enough shared memory for 2 stages");
   p.n_stages = n_stages;
-  const size_t smem = gemm_smem_bytes(bn, split, n_stages);
+  const size_t smem = gemm_smem_bytes(bn, split, n_stages, two_cta);
   const int tiles = mcast ? ((tiles_m_ + 1) / 2) * tiles_n_ : tiles_m_ * tiles_n_;  // work units
   int grid = tiles < c->sm_count ? tiles : c->sm_count;
-  if (mcast) grid = 2 * (tiles < c->sm_count / 2 ? tiles : c->sm_count / 2);
+  if (mcast || two_cta) grid = 2 * (tiles < c->sm_count / 2 ? tiles : c->sm_count / 2);
   GemmLaunch l;
   l.act = d->act; l.glu = d->glu != 0; l.mul = d->mul != nullptr; l.res = d->residual != nullptr;
   l.o32 = d->out_f32 != nullptr; l.o16 = d->out_hi != nullptr; l.dtype = d->dtype;

@@ -33,6 +33,7 @@ struct alignas(64) GemmParams {
   int block_n;      // multiple of 32 (64 in GLU mode), <= 256
   int n_stages;
   int mcast;        // 1: launched as 2-CTA clusters; the pair shares one B tile (each CTA TMA-multicasts half of it)
+  int two_cta;      // 1: launched as 2-CTA clusters running cta_group::2 MMAs (M = 256 per pair; each CTA holds half of B)
   int split;        // 0: hi*hi only, 1: three-term fp16 split product, 2: fp16 hi*hi + two fp8 cross terms
   int dtype;        // DT_F16 / DT_BF16 (operand and 16-bit output format)
   int glu;          // 1: out[:, t*bn/2 + c] = act(acc[c]+bias[c]) * (acc[bn/2+c]+bias[bn/2+c]) per tile t
@@ -188,13 +189,16 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_ro
   }
 }
 
-template <class E>
+// TWO_CTA instantiations contain cta_group::2 instructions and MUST be launched as 2-CTA clusters; the others run as single
+// CTAs or (p.mcast) as 2-CTA clusters that only share the B tile by TMA multicast.
+template <class E, bool TWO_CTA>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages][staging][bias 2x256 f32][barriers][tmem ptr]
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int BN = p.block_n;
-  const int b_tile_bytes = BN * 128;
+  constexpr int tc = TWO_CTA ? 1 : 0;
+  const int b_tile_bytes = (tc ? BN / 2 : BN) * 128;  // cta_group::2: this CTA stages only its half of the B tile
   const int n_parts = p.split ? 2 : 1;  // mode 2: the second "part" holds the two half-size fp8 tiles of each operand
   const int stage_bytes = (GEMM_A_TILE_BYTES + b_tile_bytes) * n_parts;
   uint8_t* stages = smem;
@@ -217,11 +221,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   // two CTAs of a cluster so that one B tile feeds both.  A CTA whose m-block falls off the end runs a ghost tile (zero-filled
   // loads, no stores) to keep the pair's barrier protocol in step.
   const int mc = p.mcast;
-  const uint32_t crank = mc ? cluster_ctarank() : 0u;
-  const int unit0 = mc ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int unit_stride = mc ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int num_tiles = (mc ? (tiles_m + 1) / 2 : tiles_m) * tiles_n;  // number of work units
-  auto unit_m0 = [&](int u) { return ((mc ? 2 * (u / tiles_n) + (int)crank : u / tiles_n)) * GEMM_BM; };
+  const bool paired = mc || tc;
+  const uint32_t crank = paired ? cluster_ctarank() : 0u;
+  const int unit0 = paired ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_stride = paired ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int num_tiles = (paired ? (tiles_m + 1) / 2 : tiles_m) * tiles_n;  // number of work units
+  auto unit_m0 = [&](int u) { return ((paired ? 2 * (u / tiles_n) + (int)crank : u / tiles_n)) * GEMM_BM; };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tm_a_hi);
@@ -237,19 +242,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.n_stages; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], 1);            // cta_group::2: the leader's barrier collects the bytes of both CTAs' loads
       mbar_init(&empty_bar[s], mc ? 2 : 1);  // mcast: both CTAs' MMAs must have drained the slot
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], GEMM_EPI_WARPS);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], tc ? 2 * GEMM_EPI_WARPS : GEMM_EPI_WARPS);  // one arrive per epilogue warp (of both CTAs)
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<GEMM_TMEM_COLS>(tmem_ptr_smem);
+  if (warp == 2) {
+    if constexpr (TWO_CTA) tmem_alloc_2cta<GEMM_TMEM_COLS>(tmem_ptr_smem); else tmem_alloc<GEMM_TMEM_COLS>(tmem_ptr_smem);
+  }
   tcgen05_fence_before();
   __syncthreads();
-  if (mc) cluster_sync_all();  // the peer's barriers are initialised before anything can arrive on them
+  if (paired) cluster_sync_all();  // the peer's barriers are initialised before anything can arrive on them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -264,9 +271,30 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = stages + (size_t)stage * stage_bytes;
-          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
           const int k0 = kb * GEMM_BK;
           uint8_t* sb = st + GEMM_A_TILE_BYTES * n_parts;
+          if constexpr (TWO_CTA) {
+            // cta_group::2: every load of both CTAs completes on the leader's full barrier
+            const uint32_t lead_full = mapa_cluster(&full_bar[stage], 0);
+            // (the peer never arrives: it cannot load into a slot before the leader's MMA released it, so its bytes always
+            //  belong to the phase the leader arms here)
+            if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * (uint32_t)stage_bytes);
+            const int brow2 = n0 + (int)crank * (BN / 2);
+            tma_load_2d_2cta(st, &p.tm_a_hi, lead_full, k0, m0);
+            tma_load_2d_2cta(sb, &p.tm_b_hi, lead_full, k0, brow2);
+            if (p.split == 1) {
+              tma_load_2d_2cta(st + GEMM_A_TILE_BYTES, &p.tm_a_lo, lead_full, k0, m0);
+              tma_load_2d_2cta(sb + b_tile_bytes, &p.tm_b_lo, lead_full, k0, brow2);
+            } else if (p.split == 2) {
+              tma_load_2d_2cta(st + GEMM_A_TILE_BYTES, &p.tm_a_lo, lead_full, k0, m0);
+              tma_load_2d_2cta(st + GEMM_A_TILE_BYTES + GEMM_A_TILE_BYTES / 2, &p.tm_a_hi8, lead_full, k0, m0);
+              tma_load_2d_2cta(sb + b_tile_bytes, &p.tm_b_hi8, lead_full, k0, brow2);
+              tma_load_2d_2cta(sb + b_tile_bytes + b_tile_bytes / 2, &p.tm_b_lo, lead_full, k0, brow2);
+            }
+            if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+            continue;
+          }
+          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
           // B: whole tile, or (mcast) this CTA's half of the rows, multicast to both CTAs of the pair
           const int bh = mc ? BN / 2 : 0;  // rows per half
           const int brow = n0 + (int)crank * bh;
@@ -290,11 +318,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (cta_group::2: the leader CTA issues for the pair) =====================
+    if (lane == 0 && !(tc && crank != 0)) {
       const uint32_t fmt = (p.dtype == DT_BF16) ? 1u : 0u;
+      const uint32_t mma_m = tc ? 2 * GEMM_BM : GEMM_BM;
       // c_format F32 (bit 4) | a_format [7,10) | b_format [10,13) | K-major A,B | N>>3 [17,23) | M>>4 [24,29)
-      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((mma_m >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
       int ab = 0;
@@ -310,6 +339,31 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           const uint32_t b_hi = a_hi + GEMM_A_TILE_BYTES * n_parts;
           const uint64_t da_hi = make_sw128_kmajor_desc(a_hi);
           const uint64_t db_hi = make_sw128_kmajor_desc(b_hi);
+          if constexpr (TWO_CTA) {
+#pragma unroll
+            for (int k = 0; k < GEMM_BK / 16; ++k) umma_f16_2cta(d_tmem, da_hi + 2 * k, db_hi + 2 * k, idesc, (kb | k) != 0);
+            if (p.split == 1) {
+              const uint64_t da_lo = make_sw128_kmajor_desc(a_hi + GEMM_A_TILE_BYTES);
+              const uint64_t db_lo = make_sw128_kmajor_desc(b_hi + b_tile_bytes);
+#pragma unroll
+              for (int k = 0; k < GEMM_BK / 16; ++k) umma_f16_2cta(d_tmem, da_lo + 2 * k, db_hi + 2 * k, idesc, 1u);
+#pragma unroll
+              for (int k = 0; k < GEMM_BK / 16; ++k) umma_f16_2cta(d_tmem, da_hi + 2 * k, db_lo + 2 * k, idesc, 1u);
+            } else if (p.split == 2) {
+              const uint32_t idesc8 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((mma_m >> 4) << 24);
+              const uint64_t da_lo8 = make_sw64_kmajor_desc(a_hi + GEMM_A_TILE_BYTES);
+              const uint64_t da_hi8 = make_sw64_kmajor_desc(a_hi + GEMM_A_TILE_BYTES + GEMM_A_TILE_BYTES / 2);
+              const uint64_t db_hi8 = make_sw64_kmajor_desc(b_hi + b_tile_bytes);
+              const uint64_t db_lo8 = make_sw64_kmajor_desc(b_hi + b_tile_bytes + b_tile_bytes / 2);
+#pragma unroll
+              for (int k = 0; k < GEMM_BK / 32; ++k) umma_f8_2cta(d_tmem, da_lo8 + 2 * k, db_hi8 + 2 * k, idesc8, 1u);
+#pragma unroll
+              for (int k = 0; k < GEMM_BK / 32; ++k) umma_f8_2cta(d_tmem, da_hi8 + 2 * k, db_lo8 + 2 * k, idesc8, 1u);
+            }
+            umma_commit_2cta_mcast(&empty_bar[stage], (uint16_t)3);  // frees the slot in both CTAs
+            if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+            continue;
+          }
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k)  // +32 B per K=16 step inside the 128 B swizzle row
             umma_f16(d_tmem, da_hi + 2 * k, db_hi + 2 * k, idesc, (kb | k) != 0);
@@ -336,7 +390,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           if (mc) umma_commit_mcast(&empty_bar[stage], (uint16_t)3); else umma_commit(&empty_bar[stage]);
           if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[ab]);  // accumulator complete -> epilogue
+        if constexpr (TWO_CTA) umma_commit_2cta_mcast(&tmem_full[ab], (uint16_t)3);  // both CTAs' epilogues
+        else umma_commit(&tmem_full[ab]);                                            // accumulator complete -> epilogue
         if (++ab == 2) { ab = 0; aphase ^= 1; }
       }
     }
@@ -382,22 +437,25 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       epilogue_tile<E>(p, t_row, sb, st, lane, ehalf, m0 + we * 32, tn, bn_out, n_out);
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[ab]);
+      if (lane == 0) {
+        if (tc && crank != 0) mbar_arrive_cluster(mapa_cluster(&tmem_empty[ab], 0));  // the leader's MMA waits for both CTAs
+        else mbar_arrive(&tmem_empty[ab]);
+      }
       if (++ab == 2) { ab = 0; aphase ^= 1; }
     }
   }
 
   tcgen05_fence_before();
   __syncthreads();
-  if (mc) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it / arrive on its barriers
+  if (paired) cluster_sync_all();  // no CTA leaves while its peer may still write into it / arrive on its barriers
   if (warp == 2) {
     tcgen05_fence_after();
-    tmem_dealloc<GEMM_TMEM_COLS>(tmem_base);
+    if constexpr (TWO_CTA) tmem_dealloc_2cta<GEMM_TMEM_COLS>(tmem_base); else tmem_dealloc<GEMM_TMEM_COLS>(tmem_base);
   }
 }
 
-inline size_t gemm_smem_bytes(int block_n, int split, int n_stages) {
-  const size_t stage = (size_t)(GEMM_A_TILE_BYTES + block_n * 128) * (split ? 2 : 1);
+inline size_t gemm_smem_bytes(int block_n, int split, int n_stages, int two_cta = 0) {
+  const size_t stage = (size_t)(GEMM_A_TILE_BYTES + (two_cta ? block_n / 2 : block_n) * 128) * (split ? 2 : 1);
   return 1024 /*align slack*/ + n_stages * stage + GEMM_STAGING_BYTES + 512 * 4 + (2 * GEMM_MAX_STAGES + 4) * 8 + 16;
 }
 

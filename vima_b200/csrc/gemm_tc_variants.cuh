@@ -25,15 +25,15 @@ cudaError_t launch_gemm_tc_dt(const GemmParams& p, const GemmLaunch& l, int grid
 cudaError_t launch_gemm_tc_f16(const GemmParams& p, const GemmLaunch& l, int grid, size_t smem, int max_smem, cudaStream_t stream);
 cudaError_t launch_gemm_tc_bf16(const GemmParams& p, const GemmLaunch& l, int grid, size_t smem, int max_smem, cudaStream_t stream);
 
-template <class E>
-inline cudaError_t launch_one(const GemmParams& p, int grid, size_t smem, int max_smem, cudaStream_t stream) {
+template <class E, bool TWO_CTA>
+inline cudaError_t launch_kernel(const GemmParams& p, int grid, size_t smem, int max_smem, cudaStream_t stream) {
   static bool attr_set = false;  // per instantiation, per process (one device per process)
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<E, TWO_CTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  if (p.mcast) {
+  if (p.mcast || TWO_CTA) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(GEMM_THREADS);
@@ -46,10 +46,15 @@ inline cudaError_t launch_one(const GemmParams& p, int grid, size_t smem, int ma
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<E>, p);
+    return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<E, TWO_CTA>, p);
   }
-  gemm_tc_kernel<E><<<grid, GEMM_THREADS, smem, stream>>>(p);
+  gemm_tc_kernel<E, TWO_CTA><<<grid, GEMM_THREADS, smem, stream>>>(p);
   return cudaGetLastError();
+}
+
+template <class E>
+inline cudaError_t launch_one(const GemmParams& p, int grid, size_t smem, int max_smem, cudaStream_t stream) {
+  return p.two_cta ? launch_kernel<E, true>(p, grid, smem, max_smem, stream) : launch_kernel<E, false>(p, grid, smem, max_smem, stream);
 }
 
 template <int DT>
