@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3")
-    ap.add_argument("--precision", default="f16x3")
+    ap.add_argument("--precision", default="f16f8")
     ap.add_argument("--batch", type=int, default=0, help="episodes per GPU (default: the workload's)")
     ap.add_argument("--cpu-episodes", type=int, default=4, help="episodes in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -1,0 +1,68 @@
+"""GPU, BASELINE.json full sizes (cfg3: 200M, 256 episodes, L=263, Lp=256): size-independent properties, no oracle needed.
+
+  * batch-slice consistency: episodes are independent, so the first episodes of the 256-episode batch must come out the same
+    as when they are run alone (different M, tile counts, cluster pairing -> same bits per element);
+  * masked-prompt / padded-object perturbations are exactly invisible;
+  * action indices are int64 in range, masks bool, everything finite.
+"""
+import dataclasses
+
+import pytest
+import torch
+
+from oracle import detgen, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def setup():
+    import vima_b200
+    from tests.policy_runner import build_policy
+
+    vima_b200.set_precision("f16x3")
+    case = synth.CASES["cfg3"]
+    pol = build_policy(case.model)
+    E = 768
+    B, T, Q, Lp = case.B, case.T, case.Q, case.Lp
+    obs = (detgen.uniform("fs.obs", (T, B, Q, E)) * 1.5).cuda()
+    act = (detgen.uniform("fs.act", (T - 1, B, E)) * 1.5).cuda()
+    prm = (detgen.uniform("fs.prompt", (Lp, B, E)) * 1.5).cuda()
+    om = (detgen.randint("fs.om", (T, B, Q), 0, 5) > 0).cuda()
+    om[:, :, 0] = True
+    pm = torch.ones(B, Lp, dtype=torch.bool, device="cuda")
+    pm[1::2, 200:] = False  # every other prompt is 200 tokens long
+    return pol, obs, om, act, prm, pm
+
+
+def test_full_size_step_is_finite_and_typed(setup):
+    pol, obs, om, act, prm, pm = setup
+    with torch.no_grad():
+        pred = pol.forward(obs_token=obs, obs_mask=om, action_token=act, prompt_token=prm, prompt_token_mask=pm)
+        dists = pol.forward_action_decoder(pred[-1:])
+    assert pred.shape == (8, 256, 768) and torch.isfinite(pred).all()
+    for k, d in dists.items():
+        m = d.mode()
+        assert m.dtype == torch.int64 and m.shape[:2] == (1, 256)
+        hi = torch.tensor([50, 100] if k.endswith("position") else [50] * 4, device="cuda")
+        assert (m >= 0).all() and (m < hi).all()
+
+
+def test_batch_slice_consistency(setup):
+    pol, obs, om, act, prm, pm = setup
+    with torch.no_grad():
+        full = pol.forward(obs_token=obs, obs_mask=om, action_token=act, prompt_token=prm, prompt_token_mask=pm)
+        n = 6
+        part = pol.forward(obs_token=obs[:, :n].contiguous(), obs_mask=om[:, :n].contiguous(), action_token=act[:, :n].contiguous(),
+                           prompt_token=prm[:, :n].contiguous(), prompt_token_mask=pm[:n].contiguous())
+    assert torch.equal(full[:, :n], part), (full[:, :n] - part).abs().max().item()
+
+
+def test_padding_is_exactly_invisible_at_full_size(setup):
+    pol, obs, om, act, prm, pm = setup
+    with torch.no_grad():
+        base = pol.forward(obs_token=obs, obs_mask=om, action_token=act, prompt_token=prm, prompt_token_mask=pm)
+        prm2 = prm.clone()
+        prm2[200:, 1::2] += 7.0  # masked prompt tokens
+        pert = pol.forward(obs_token=obs, obs_mask=om, action_token=act, prompt_token=prm2, prompt_token_mask=pm)
+    assert torch.equal(base, pert)
