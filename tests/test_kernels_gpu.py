@@ -317,6 +317,37 @@ def test_attention_fully_masked_prefix(ctx):
     assert rel(merge(o_hi, o_lo, tdt, E), ref) < 1e-5
 
 
+@pytest.mark.parametrize("L0,Ln", [(0, 33), (66, 33), (230, 33), (131, 1)])
+def test_attention_kv_cache_addressing(ctx, L0, Ln):
+    """Incremental decode: Ln new queries at positions L0.. attend causally over a cache with row pitch Lmax per episode
+    (kv_batch_rows / mask_ld / q_pos0); equals the matching rows of the full-history causal attention."""
+    dt, tdt = DT["f16"]
+    B, H, D, Lmax = 3, 4, 32, 263
+    E = H * D
+    L = L0 + Ln
+    g = torch.Generator(device="cuda").manual_seed(11)
+    qkv_full = torch.randn(B, Lmax, 3 * E, device="cuda", generator=g)
+    key_mask = torch.rand(B, Lmax, device="cuda", generator=g) > 0.2
+    key_mask[:, 0] = True
+    # cache layout: [B*Lmax, 2E] (K | V); rows >= L hold junk that must not be read as valid keys
+    cache = qkv_full[:, :, E:].clone()
+    cache[:, L:] = 1e4
+    ch, cl, ldc = split_ops(ctx, cache.reshape(B * Lmax, 2 * E), dt, True)
+    qn = qkv_full[:, L0:L, :E].reshape(B * Ln, E).contiguous()
+    qh, ql, ldq = split_ops(ctx, qn, dt, True)
+    o_hi = torch.zeros(B * Ln, E, dtype=torch.int16, device="cuda"); o_lo = torch.zeros_like(o_hi)
+    ctx.attention(q=(qh, ql, ldq, 0), k=(ch, cl, ldc, 0), v=(ch, cl, ldc, E), o=(o_hi, o_lo, E, 0), B=B, H=H, Lq=Ln, Lk=L, D=D,
+                  scale=1 / math.sqrt(D), causal=True, key_mask=key_mask.to(torch.uint8), dtype=dt, kv_batch_rows=Lmax, mask_ld=Lmax, q_pos0=L0)
+    hd = lambda x, n: x.reshape(B, n, H, D).permute(0, 2, 1, 3).double()
+    full = qkv_full[:, :L]
+    ref = ref_attention(hd(full[..., :E], L), hd(full[..., E:2 * E], L), hd(full[..., 2 * E:], L), 1 / math.sqrt(D), True, key_mask[:, :L], None)
+    ref = ref[:, :, L0:L].permute(0, 2, 1, 3).reshape(B * Ln, E)
+    assert rel(merge(o_hi, o_lo, tdt, E), ref) < 1e-5
+    with pytest.raises(RuntimeError):
+        ctx.attention(q=(qh, ql, ldq, 0), k=(ch, cl, ldc, 0), v=(ch, cl, ldc, E), o=(o_hi, o_lo, E, 0), B=B, H=H, Lq=Ln, Lk=L, D=D,
+                      scale=1 / math.sqrt(D), causal=True, dtype=dt, kv_batch_rows=Lmax, q_pos0=-1)
+
+
 def test_small_attention(ctx):
     N, S, H, W = 37, 5, 24, 768
     g = torch.Generator(device="cuda").manual_seed(1)

@@ -64,14 +64,17 @@ __global__ void __launch_bounds__(256, (D == 32) ? 2 : 1) attention_kernel(const
   float* sbias = reinterpret_cast<float*>(qb_counter + 1);     // [2*Lk-1] (log2 domain) when rel_bias
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int kvb = p.kv_batch_rows ? p.kv_batch_rows : Lk;
+  const int mld = p.mask_ld ? p.mask_ld : Lk;
+  const int qp0 = p.q_pos0;
   // ---- stage K (row-major) and V (transposed) of this (b, h) in shared memory ----
   constexpr int CH = D / 8;  // 16-byte chunks per row
   for (int idx = tid; idx < Lk_pad * CH; idx += 256) {
     const int j = idx / CH, c = idx % CH;
     uint4 kh = make_uint4(0, 0, 0, 0), kl = kh, vh = kh, vl = kh;
     if (j < Lk) {
-      const size_t rk = (size_t)(b * Lk + j) * p.ldk + h * D + c * 8;
-      const size_t rv = (size_t)(b * Lk + j) * p.ldv + h * D + c * 8;
+      const size_t rk = ((size_t)b * kvb + j) * p.ldk + h * D + c * 8;
+      const size_t rv = ((size_t)b * kvb + j) * p.ldv + h * D + c * 8;
       kh = __ldg(reinterpret_cast<const uint4*>(p.k_hi + rk));
       vh = __ldg(reinterpret_cast<const uint4*>(p.v_hi + rv));
       if (SPLIT) {
@@ -91,7 +94,7 @@ __global__ void __launch_bounds__(256, (D == 32) ? 2 : 1) attention_kernel(const
   }
   for (int j = tid; j < Lk_pad; j += 256) {
     float m = -INFINITY;  // beyond the sequence: excluded
-    if (j < Lk) m = (p.key_mask == nullptr || p.key_mask[(size_t)b * Lk + j]) ? 0.f : FP32_MIN;
+    if (j < Lk) m = (p.key_mask == nullptr || p.key_mask[(size_t)b * mld + j]) ? 0.f : FP32_MIN;
     maskadd[j] = m;
   }
   if (p.rel_bias)
@@ -171,7 +174,7 @@ __global__ void __launch_bounds__(256, (D == 32) ? 2 : 1) attention_kernel(const
       }
       // ---- log2-domain scores; bias / soft causal mask / key mask only where the tile needs them ----
       const bool needs_mask = !tile_plain[kt];
-      const bool needs_causal = p.causal && (kt * 64 + 63 > qb * 16);
+      const bool needs_causal = p.causal && (kt * 64 + 63 > qb * 16 + qp0);
       float mx[2] = {-INFINITY, -INFINITY};
       if (!needs_mask && !needs_causal && p.rel_bias == nullptr) {
 #pragma unroll
@@ -192,7 +195,7 @@ __global__ void __launch_bounds__(256, (D == 32) ? 2 : 1) attention_kernel(const
             const int i = (e & 2) ? r1 : r0;
             float y = s[nt][e] * c_l2;
             if (p.rel_bias && j < Lk) y += sbias[j - min(i, Lq - 1) + Lk - 1];
-            if (needs_causal && j > i) y = CAUSAL_L2;
+            if (needs_causal && j > i + qp0) y = CAUSAL_L2;
             if (needs_mask) y += maskadd[j];
             s[nt][e] = y;
             mx[e >> 1] = fmaxf(mx[e >> 1], y);
@@ -261,7 +264,7 @@ __global__ void __launch_bounds__(256, (D == 32) ? 2 : 1) attention_kernel(const
       }
       // Every later key tile is causally masked for all 16 rows: its weights are exp(-1e4 - m), exactly 0 in
       // fp32 once m > -1e4 + 104, so stopping here is bit-identical to the reference's full-width softmax.
-      if (p.causal && (kt + 1) * 64 > qb * 16 + 15) {
+      if (p.causal && (kt + 1) * 64 > qb * 16 + 15 + qp0) {
         const bool done = (mrow[0] > EXIT_L2) && (mrow[1] > EXIT_L2);
         if (__all_sync(0xffffffffu, done)) break;
       }

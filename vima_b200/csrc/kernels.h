@@ -28,6 +28,9 @@ struct AttnParams {
   int B, H, Lq, Lk, D;
   float scale; int causal; int split; int dtype;
   unsigned char *o_lo8, *o_hi8; int ldo8;      // e4m3 cross-term views of the output, optional
+  int kv_batch_rows;                           // rows between consecutive batch elements in k/v (>= Lk; KV caches), 0 = Lk
+  int mask_ld;                                 // row pitch of key_mask, 0 = Lk
+  int q_pos0;                                  // causal: query row i sits at key position q_pos0 + i (incremental decode)
 };
 cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream);
 
@@ -72,6 +75,12 @@ cudaError_t launch_bbox_norm(const long long* bbox, long long n, float* out, cud
 cudaError_t launch_fill_ee(const long long* ee, const float* table, long long n_te, int Q, unsigned short* hi, unsigned short* lo,
                            int ld16, int col0, int n_pad, int dtype, cudaStream_t s);
 cudaError_t launch_action_scale(const long long* idx, long long n, int width, const float* inv_bins, float* out, cudaStream_t s);
+cudaError_t launch_object_stats(const void* segm, int elem, int n_img, int H, int W, const long long* ids, int n_obj, int ids_per_image,
+                                int* stats, cudaStream_t s);
+cudaError_t launch_crop_resize(const unsigned char* rgb, int n_img, int H, int W, const int* stats, int n_obj, unsigned char* crops,
+                               long long* bbox, unsigned char* mask, int* n_valid, cudaStream_t s);
+cudaError_t launch_action_post(const long long* idx, long long n, int width, const float* bins, const float* lo, const float* hi,
+                               int bound_stride, float* out, cudaStream_t s);
 cudaError_t launch_head_select(const float* logits, int B, int n_heads, const int* head_off, float* logits_norm, long long* modes,
                                cudaStream_t s);
 cudaError_t launch_gato_positions(const unsigned char* prompt_mask, int B, int Lp, int L, unsigned char* mask_out, long long* pos_out,

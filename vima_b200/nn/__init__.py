@@ -11,4 +11,4 @@ from .action import (
 from .basic import Conv1D, Embedding, Linear, MLPSequential, build_mlp
 from .obj_encoder import GatoMultiViewRGBEncoder, GatoViTEncoder, ObjEncoder, ViTEncoder, VisionTransformer
 from .t5_encoder import T5PromptEncoder, WordEmbedding
-from .xattn_gpt import HFGPT, XAttnGPT
+from .xattn_gpt import HFGPT, DecodeCache, XAttnGPT

@@ -62,17 +62,52 @@ def pack_block(ctx, blk: "Block", p) -> dict:
     }
 
 
-def run_block(ctx, p, W, blk: "Block", x32, x16, c16, *, B, L, E, H, omask, chain_ln=None, want16=False, out_f32=None):
+class DecodeCache:
+    """Per-layer K/V cache of one batch of episodes for step-by-step decode.
+
+    The reference re-runs the whole history every environment step (scripts/example.py:139-171); with the cache a step
+    only pushes its Q+1 new tokens through the stack: the prompt's key/value projections are computed once, and every
+    causal block appends the new tokens' keys/values to `kv[i]` ([B*Lmax, 2E] (hi, lo) pairs) and attends over the
+    cached prefix (`vima_attention` with kv_batch_rows / mask_ld / q_pos0)."""
+
+    def __init__(self, *, B: int, Lmax: int, E: int, n_layer: int, device, split: bool):
+        self.B, self.Lmax, self.E, self.L = B, Lmax, E, 0
+        mk = lambda: torch.zeros((B * Lmax, 2 * E), dtype=torch.int16, device=device)
+        self.kv_hi = [mk() for _ in range(n_layer)]
+        self.kv_lo = [mk() if split else None for _ in range(n_layer)]
+        self.mask = torch.zeros((B, Lmax), dtype=torch.uint8, device=device)
+        self.n_valid = torch.zeros((B,), dtype=torch.int64, device=device)  # valid tokens so far -> next position id
+        self.prompt_kv = None  # per-layer projected prompt keys/values (filled by the first step)
+
+    def append_kv(self, i: int, qkv16, L0: int, Ln: int):
+        E, B = self.E, self.B
+        self.kv_hi[i].view(B, self.Lmax, 2 * E)[:, L0:L0 + Ln].copy_(qkv16.hi.view(B, Ln, -1)[:, :, E:3 * E])
+        if self.kv_lo[i] is not None:
+            self.kv_lo[i].view(B, self.Lmax, 2 * E)[:, L0:L0 + Ln].copy_(qkv16.lo.view(B, Ln, -1)[:, :, E:3 * E])
+
+
+def run_block(ctx, p, W, blk: "Block", x32, x16, c16, *, B, L, E, H, omask, chain_ln=None, want16=False, out_f32=None, cache=None,
+              layer=0):
     """GPT-1 post-LN block (components.py:23-37 / gpt.py:223-249): returns (LN2 output fp32, operands of the NEXT consumer):
-    with `chain_ln` the operands are chain_ln(LN2(...)) (next layer's query LayerNorm), with `want16` they are LN2(...) itself."""
+    with `chain_ln` the operands are chain_ln(LN2(...)) (next layer's query LayerNorm), with `want16` they are LN2(...) itself.
+    With `cache` the L rows are the NEW tokens of each episode and attention runs over the cached prefix + themselves."""
     M = B * L
     d = E // H
     # operand formats: attention inputs keep the 16-bit (hi, lo) pair; everything that only feeds a GEMM carries e4m3
     # cross-term views in "f16f8" mode (out_f8=True is a no-op in the other modes)
     _, qkv16 = eng.gemm(ctx, x16, W["c_attn"], p, want16=True)
-    ctx.attention(q=(qkv16.hi, qkv16.lo, qkv16.ld, 0), k=(qkv16.hi, qkv16.lo, qkv16.ld, E), v=(qkv16.hi, qkv16.lo, qkv16.ld, 2 * E),
-                  o=(c16.hi, c16.lo, c16.ld, 0), B=B, H=H, Lq=L, Lk=L, D=d, scale=1.0 / math.sqrt(d), causal=True, key_mask=omask, dtype=p.dtype,
-                  o8=None if c16.lo8 is None else (c16.lo8, c16.hi8))
+    o8 = None if c16.lo8 is None else (c16.lo8, c16.hi8)
+    if cache is None:
+        ctx.attention(q=(qkv16.hi, qkv16.lo, qkv16.ld, 0), k=(qkv16.hi, qkv16.lo, qkv16.ld, E), v=(qkv16.hi, qkv16.lo, qkv16.ld, 2 * E),
+                      o=(c16.hi, c16.lo, c16.ld, 0), B=B, H=H, Lq=L, Lk=L, D=d, scale=1.0 / math.sqrt(d), causal=True, key_mask=omask,
+                      dtype=p.dtype, o8=o8)
+    else:
+        L0 = cache.L
+        cache.append_kv(layer, qkv16, L0, L)
+        khi, klo = cache.kv_hi[layer], cache.kv_lo[layer]
+        ctx.attention(q=(qkv16.hi, qkv16.lo, qkv16.ld, 0), k=(khi, klo, 2 * E, 0), v=(khi, klo, 2 * E, E), o=(c16.hi, c16.lo, c16.ld, 0),
+                      B=B, H=H, Lq=L, Lk=L0 + L, D=d, scale=1.0 / math.sqrt(d), causal=True, key_mask=cache.mask, dtype=p.dtype, o8=o8,
+                      kv_batch_rows=cache.Lmax, mask_ld=cache.Lmax, q_pos0=L0)
     s32, _ = eng.gemm(ctx, c16, W["c_proj"], p, residual=x32, want_f32=True)
     n32, _, n16 = eng.norm(ctx, s32, p, rows=M, cols=E, w=blk.ln_1.weight.detach(), b=blk.ln_1.bias.detach(), eps=blk.ln_1.eps, want_f32=True,
                            want16=True, out_f8=True)
@@ -194,10 +229,13 @@ class XAttnGPT(nn.Module):
         prompt_position_ids: Optional[torch.Tensor] = None,
         batch_first: bool = False,
         obs_action_masks: Optional[torch.Tensor] = None,
+        cache: Optional[DecodeCache] = None,
     ):
+        """Reference signature (xattn_gpt.py:89-99) plus `cache`: with a DecodeCache the obs/action arguments describe only the
+        tokens appended this step (their position ids are absolute) and the return value holds only their rows."""
         ctx = eng.ctx_for(obs_action_tokens)
         p = eng.prec()
-        if not self._input_checked:
+        if not self._input_checked and cache is None:
             self._check_input(obs_action_tokens, prompt_tokens, prompt_mask, batch_first, obs_action_masks)
         dev = obs_action_tokens.device
         if batch_first:
@@ -208,6 +246,11 @@ class XAttnGPT(nn.Module):
             Lp = prompt_tokens.shape[0]
         assert E == self.embd_dim
         assert Lp <= self.xattn_n_positions and L <= self.n_positions
+        if cache is not None:
+            if obs_action_position_ids is None or obs_action_masks is None:
+                raise ValueError("cached decode needs absolute position ids and masks for the appended tokens")
+            if cache.L + L > cache.Lmax or cache.B != B or cache.E != E:
+                raise ValueError(f"DecodeCache(B={cache.B}, Lmax={cache.Lmax}) cannot take {L} more tokens at length {cache.L} for batch {B}")
         if obs_action_tokens.dtype != torch.float32 or prompt_tokens.dtype != torch.float32:
             raise TypeError("XAttnGPT expects float32 tokens (xattn_gpt.py:150,152)")
         tok = obs_action_tokens if obs_action_tokens.stride(-1) == 1 else obs_action_tokens.contiguous()
@@ -224,6 +267,8 @@ class XAttnGPT(nn.Module):
             prompt_mask = prompt_mask.squeeze(1)
         pmask = None if prompt_mask is None else eng.as_u8(prompt_mask)
         omask = None if obs_action_masks is None else eng.as_u8(obs_action_masks)
+        if cache is not None:
+            cache.mask[:, cache.L:cache.L + L].copy_(omask)
 
         M, Mp, H, Hx = B * L, B * Lp, self.n_head, self.xattn_n_head
         d_s, d_x = E // H, E // Hx
@@ -231,8 +276,11 @@ class XAttnGPT(nn.Module):
         # x = tokens + positions_embed[ids] (fp32 residual stream); kv = prompt + xattn_positions_embed[ids] (operands only)
         x32 = torch.empty((M, E), dtype=torch.float32, device=dev)
         ctx.add_pos_embed(tok, sb, sl, oa_ids, self.positions_embed.weight.detach(), B, L, E, out_f32=x32, err_flag=err)
-        kv16 = eng.Opnd(Mp, E, dev, p.split, f8=p.f8)
-        if p.f8:  # prompt + position embedding feeds only the key_value GEMM: fp32 once, then hi16 + e4m3 views
+        need_prompt = cache is None or cache.prompt_kv is None
+        kv16 = eng.Opnd(Mp, E, dev, p.split, f8=p.f8) if need_prompt else None
+        if not need_prompt:
+            pass
+        elif p.f8:  # prompt + position embedding feeds only the key_value GEMM: fp32 once, then hi16 + e4m3 views
             kv32 = torch.empty((Mp, E), dtype=torch.float32, device=dev)
             ctx.add_pos_embed(ptk, psb, psl, pr_ids, self.xattn_positions_embed.weight.detach(), B, Lp, E, out_f32=kv32, hi=kv16.hi, lo=None,
                               dtype=p.dtype, err_flag=err)
@@ -241,7 +289,7 @@ class XAttnGPT(nn.Module):
         else:
             ctx.add_pos_embed(ptk, psb, psl, pr_ids, self.xattn_positions_embed.weight.detach(), B, Lp, E, hi=kv16.hi, lo=kv16.lo,
                               dtype=p.dtype, err_flag=err)
-        if not self._input_checked:
+        if not self._input_checked and cache is None:
             if int(err.item()) != 0:
                 raise IndexError("index out of range in self (position id outside the embedding table)")
             self._input_checked = True
@@ -251,10 +299,12 @@ class XAttnGPT(nn.Module):
         # first layer's query LayerNorm; later ones are chained onto the previous block's LN2
         w, b = lnw(self.xattns[0].layernorm)
         _, _, qin16 = eng.norm(ctx, x32, p, rows=M, cols=E, w=w, b=b, eps=self.xattns[0].layernorm.eps, want16=True, out_f8=True)
+        if cache is not None and need_prompt:
+            cache.prompt_kv = [eng.gemm(ctx, kv16, W["wkv"], p, want16=True)[1] for W in layers]
         for i, (blk, xa, W) in enumerate(zip(self.h, self.xattns, layers)):
             # ---------------- XAttention ----------------
             _, q16 = eng.gemm(ctx, qin16, W["wq"], p, want16=True)
-            _, kvp16 = eng.gemm(ctx, kv16, W["wkv"], p, want16=True)
+            kvp16 = cache.prompt_kv[i] if cache is not None else eng.gemm(ctx, kv16, W["wkv"], p, want16=True)[1]
             c16 = eng.Opnd(M, E, dev, p.split, f8=p.f8)
             ctx.attention(q=(q16.hi, q16.lo, q16.ld, 0), k=(kvp16.hi, kvp16.lo, kvp16.ld, 0), v=(kvp16.hi, kvp16.lo, kvp16.ld, E),
                           o=(c16.hi, c16.lo, c16.ld, 0), B=B, H=Hx, Lq=L, Lk=Lp, D=d_x, scale=1.0 / math.sqrt(d_x), causal=False,
@@ -269,7 +319,10 @@ class XAttnGPT(nn.Module):
             del h16, a32, a16
             # ---------------- causal Block ----------------
             nxt = self.xattns[i + 1].layernorm if i + 1 < self.n_layer else None
-            x32, qin16 = run_block(ctx, p, W, blk, xb32, xb16, c16, B=B, L=L, E=E, H=H, omask=omask, chain_ln=nxt, out_f32=x32)
+            x32, qin16 = run_block(ctx, p, W, blk, xb32, xb16, c16, B=B, L=L, E=E, H=H, omask=omask, chain_ln=nxt, out_f32=x32, cache=cache,
+                                   layer=i)
+        if cache is not None:
+            cache.L += L
         out = x32.view(B, L, E)
         return out if batch_first else out.transpose(0, 1)
 

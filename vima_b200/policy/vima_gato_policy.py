@@ -168,3 +168,5 @@ class VIMAGatoPolicy(nn.Module):
 
     discretize_action = VIMAPolicy.discretize_action
     _de_discretize_actions = VIMAPolicy._de_discretize_actions
+    _bin_tensor = VIMAPolicy._bin_tensor
+    postprocess_actions = VIMAPolicy.postprocess_actions

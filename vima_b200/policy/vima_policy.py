@@ -87,6 +87,49 @@ class VIMAPolicy(nn.Module):
         return tokens_out[Q - 1 :: Q + 1]
 
     # --------------------------------------------------------------------------------------------------
+    # Incremental decode (not in the reference, which re-runs the whole history each step).
+    def start_decode(self, prompt_token: torch.Tensor, prompt_token_mask: torch.Tensor, *, max_tokens: Optional[int] = None):
+        """Open a K/V cache for a batch of episodes: prompt_token (Lp,B,E), prompt_token_mask (B,Lp); room for `max_tokens`
+        history tokens per episode (default: the decoder's n_positions).  Feed it to `forward_step` once per environment step."""
+        Lp, B, E = prompt_token.shape
+        ctx = eng.ctx_for(prompt_token)
+        Lmax = self.xattn_gpt.n_positions if max_tokens is None else int(max_tokens)
+        if not 0 < Lmax <= self.xattn_gpt.n_positions:
+            raise ValueError(f"max_tokens={Lmax} outside (0, n_positions={self.xattn_gpt.n_positions}]")
+        cache = vnn.DecodeCache(B=B, Lmax=Lmax, E=E, n_layer=self.xattn_gpt.n_layer, device=prompt_token.device, split=eng.prec().split)
+        pmask_u8 = eng.as_u8(prompt_token_mask)
+        cache.prompt = (prompt_token, pmask_u8, torch.empty(pmask_u8.shape, dtype=torch.int64, device=prompt_token.device))
+        ctx.mask_cumsum(pmask_u8, cache.prompt[2])
+        return cache
+
+    def forward_step(self, cache, obs_token: torch.Tensor, obs_mask: torch.Tensor, prev_action_token: Optional[torch.Tensor]):
+        """One environment step through the cache: obs_token (1,B,Q,E), obs_mask (1,B,Q), prev_action_token (1,B,E) (None at
+        the first step) -> predicted action token (1,B,E); equals `forward(...)[-1:]` over the whole history.  Q may differ
+        from step to step: scripts/example.py:139-171 re-pads every earlier step to the running maximum, but padded slots are
+        masked keys with weight exactly 0 that do not advance position ids, so earlier steps can stay at the width they were
+        appended with.  The prediction is read at the LAST slot passed (a padded one if the caller padded), as the reference does."""
+        ctx = eng.ctx_for(obs_token)
+        _, B, Q, E = obs_token.shape
+        if (prev_action_token is None) != (cache.L == 0):
+            raise ValueError("forward_step: exactly one action token per previous step is required")
+        dev = obs_token.device
+        new = obs_token[0].float().transpose(0, 1)  # (Q,B,E)
+        m_new = eng.as_u8(obs_mask[0])
+        if prev_action_token is not None:
+            new = torch.cat([prev_action_token.float(), new], dim=0)
+            m_new = torch.cat([torch.ones((B, 1), dtype=torch.uint8, device=dev), m_new], dim=1)
+        new, m_new = new.contiguous(), m_new.contiguous()
+        pos = torch.empty(m_new.shape, dtype=torch.int64, device=dev)
+        ctx.mask_cumsum(m_new, pos)
+        pos += cache.n_valid[:, None]
+        cache.n_valid += m_new.sum(dim=1)
+        prompt_token, pmask_u8, prompt_pos = cache.prompt
+        out = self.xattn_gpt(obs_action_tokens=new, prompt_tokens=prompt_token, prompt_mask=pmask_u8.view(torch.bool),
+                             obs_action_masks=m_new.view(torch.bool), obs_action_position_ids=pos, prompt_position_ids=prompt_pos,
+                             cache=cache)
+        return out[-1:]
+
+    # --------------------------------------------------------------------------------------------------
     def forward_prompt_assembly(self, prompts):
         """(token_types, word_batch, image_batch) -> prompt tokens (Lp,B,E), masks (B,Lp) bool  (vima_policy.py:161-240)."""
         raw_prompts_token_type, word_batch, image_batch = prompts
@@ -187,21 +230,51 @@ class VIMAPolicy(nn.Module):
             action[k] = torch.bucketize(action[k].contiguous(), br)
         return {k: v.long() for k, v in action.items()}
 
+    def postprocess_actions(self, actions, action_bounds_low: torch.Tensor, action_bounds_high: torch.Tensor):
+        """The environment-facing step after the heads, scripts/example.py:199-232, in one kernel per action key: int64 bin
+        indices -> de-discretised, scaled to the action bounds and clamped positions; rotations mapped to [-1, 1].
+        Bounds: float32 (..., 2) broadcast over the leading dims of the position indices, or one row per episode."""
+        out = {}
+        for k, v in actions.items():
+            ctx = eng.ctx_for(v)
+            width = v.shape[-1]
+            idx = v.to(torch.int64).contiguous()
+            n = idx.numel() // width
+            if k.endswith("position"):
+                bins = self._bin_tensor(True, width, v.device)
+                lo = action_bounds_low.to(device=v.device, dtype=torch.float32).reshape(-1, width).contiguous()
+                hi = action_bounds_high.to(device=v.device, dtype=torch.float32).reshape(-1, width).contiguous()
+                if lo.shape != hi.shape or lo.shape[0] not in (1, n):
+                    raise ValueError(f"action bounds must hold 1 or {n} rows of {width} values, got {tuple(lo.shape)} / {tuple(hi.shape)}")
+                stride = 0 if lo.shape[0] == 1 else width
+            else:
+                bins = self._bin_tensor(False, width, v.device)
+                key = ("rot_bounds", width, str(v.device))
+                if key not in self._bins:
+                    self._bins[key] = (torch.full((1, width), -1.0, device=v.device), torch.full((1, width), 1.0, device=v.device))
+                lo, hi = self._bins[key]
+                stride = 0
+            o = torch.empty(idx.shape, dtype=torch.float32, device=v.device)
+            ctx.action_postprocess(idx.view(-1, width), n, width, bins, lo, hi, stride, o)
+            out[k] = o
+        return out
+
+    def _bin_tensor(self, is_position: bool, width: int, device):
+        key = (is_position, width, str(device))
+        if key not in self._bins:
+            b = [float(self._n_discrete_x_bins), float(self._n_discrete_y_bins)] if is_position else [float(self._n_discrete_rot_bins)] * width
+            self._bins[key] = torch.tensor(b, dtype=torch.float32).to(device)
+        return self._bins[key]
+
     def _de_discretize_actions(self, actions):
         """int64 indices -> float / bins  (vima_policy.py:301-322)."""
         out = {}
         for k, v in actions.items():
             ctx = eng.ctx_for(v)
             width = v.shape[-1]
-            key = (k.endswith("position"), width, str(v.device))
-            if key not in self._bins:
-                if k.endswith("position"):
-                    b = [float(self._n_discrete_x_bins), float(self._n_discrete_y_bins)]
-                else:
-                    b = [float(self._n_discrete_rot_bins)] * width
-                self._bins[key] = torch.tensor(b, dtype=torch.float32).to(v.device)
+            bins = self._bin_tensor(k.endswith("position"), width, v.device)
             idx = v.to(torch.int64).contiguous()
             o = torch.empty(idx.shape, dtype=torch.float32, device=v.device)
-            ctx.action_scale(idx.view(-1, width), idx.numel() // width, width, self._bins[key], o)
+            ctx.action_scale(idx.view(-1, width), idx.numel() // width, width, bins, o)
             out[k] = o
         return out
