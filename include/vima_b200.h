@@ -29,7 +29,7 @@ extern "C" {
 #endif
 #pragma GCC visibility push(default)
 
-#define VIMA_B200_ABI_VERSION 2
+#define VIMA_B200_ABI_VERSION 3
 
 enum { VIMA_OK = 0, VIMA_E_INVALID = 1, VIMA_E_CUDA = 2, VIMA_E_UNSUPPORTED = 3 };
 enum { VIMA_DT_F16 = 0, VIMA_DT_BF16 = 1 };
@@ -147,6 +147,9 @@ typedef struct {
   int causal;
   int dtype;
   void *o_lo8, *o_hi8; int ldo8; /* optional e4m3 cross-term views of the output */
+  /* KV-cache addressing (incremental decode): k/v rows of batch element b start at b*kv_batch_rows (0 = Lk),
+   * key_mask rows have pitch mask_ld (0 = Lk), and under `causal` query row i sits at key position q_pos0 + i. */
+  int kv_batch_rows, mask_ld, q_pos0;
 } vima_attn_desc;
 int vima_attention(vima_ctx*, const vima_attn_desc* d, void* stream);
 
@@ -190,9 +193,26 @@ int vima_fill_ee(vima_ctx*, const int64_t* ee, const float* table, int64_t n_te,
 /* preprocess.py:28 range check: *out_max = max(*out_max, max(x)) (device int). */
 int vima_max_u8(vima_ctx*, const uint8_t* x, int64_t n, int* out_max, void* stream);
 
+/* ---- observation / prompt-asset preparation: the step before the path (scripts/example.py:243-473) ------------- */
+/* example.py:409-416 / 279-286: per (image, object id) pixel count and bounding box of `segm == id`.
+ * segm [n_img,H,W] with 1-, 4- or 8-byte integer elements; obj_ids_dev int64 [n_obj] (shared) or [n_img,n_obj] when
+ * ids_per_image; stats int32 [n_img,n_obj,5] = {count, xmin, xmax, ymin, ymax}.  n_obj <= 64. */
+int vima_object_stats(vima_ctx*, const void* segm, int segm_elem_bytes, int n_img, int H, int W, const int64_t* obj_ids_dev, int n_obj,
+                      int ids_per_image, int32_t* stats, void* stream);
+/* example.py:412-456: for every object with >= 2 pixels: bbox [int((xmin+xmax)/2), int((ymin+ymax)/2), ymax-ymin, xmax-xmin],
+ * crop of rgb [n_img,3,H,W] u8, zero-pad to a square, cv2.resize(.., (32,32), INTER_AREA) (bit-exact with OpenCV's 8-bit
+ * code paths); visible objects first, zero-filled slots after.  crops u8 [n_img,n_obj,3,32,32], bbox int64 [n_img,n_obj,4],
+ * mask u8 [n_img,n_obj], n_valid int32 [n_img] (optional). */
+int vima_crop_resize(vima_ctx*, const uint8_t* rgb, int n_img, int H, int W, const int32_t* stats, int n_obj, uint8_t* crops,
+                     int64_t* bbox, uint8_t* mask, int32_t* n_valid, void* stream);
+
 /* ---- action heads -------------------------------------------------------------------------------------------- */
 /* vima_policy.py:301-322: out[i,c] = float(idx[i,c]) / bins[c] */
 int vima_action_scale(vima_ctx*, const int64_t* idx, int64_t n, int width, const float* bins_dev, float* out, void* stream);
+/* scripts/example.py:199-232 (the step after the path): out[i,c] = clamp(idx[i,c]/bins[c] * (hi-lo) + lo, lo, hi), lo/hi
+ * [n or 1, width] fp32 on the device (bound_stride 0 = one broadcast row); rotations use lo=-1, hi=1. */
+int vima_action_postprocess(vima_ctx*, const int64_t* idx, int64_t n, int width, const float* bins_dev, const float* lo_dev,
+                            const float* hi_dev, int bound_stride, float* out, void* stream);
 /* dists.py:20-28: per head log-softmax normalised logits and mode (first argmax of probs). head_off: DEVICE int[n_heads+1]. */
 int vima_head_select(vima_ctx*, const float* logits, int B, int n_heads, const int32_t* head_off_dev, float* logits_norm, int64_t* modes,
                      void* stream);

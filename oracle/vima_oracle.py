@@ -416,6 +416,22 @@ def forward_action_token(sd: SD, actions: Dict[str, torch.Tensor]) -> torch.Tens
     return linear(torch.cat(feats, dim=-1), sd["action_encoder._post_layer.weight"], sd["action_encoder._post_layer.bias"])
 
 
+def postprocess_actions(actions: Dict[str, torch.Tensor], bounds_low: torch.Tensor, bounds_high: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """The environment-facing arithmetic after the heads, scripts/example.py:199-232: `_de_discretize_actions`
+    (vima_policy.py:301-322), positions scaled into the action bounds and clamped, rotations mapped to [-1, 1]."""
+    a = {k: v.float().clone() for k, v in actions.items()}
+    for k in ("pose0_position", "pose1_position"):
+        a[k][..., 0] = a[k][..., 0] / 50
+        a[k][..., 1] = a[k][..., 1] / 100
+        a[k] = a[k] * (bounds_high - bounds_low) + bounds_low
+        a[k] = torch.clamp(a[k], min=bounds_low, max=bounds_high)
+    for k in ("pose0_rotation", "pose1_rotation"):
+        a[k] = a[k] / 50
+        a[k] = a[k] * 2 - 1
+        a[k] = torch.clamp(a[k], min=-1, max=1)
+    return a
+
+
 def policy_step(sd: SD, *, obs, history_obs_tokens, history_obs_masks, history_action_tokens, prompt_tokens,
                 prompt_masks, n_head: int, xattn_n_head: int):
     """One policy step as scripts/example.py:125-198 runs it (full-history re-forward)."""

@@ -127,3 +127,30 @@ def test_module_level_xattn_gpt_defaults():
                                   obs_action_masks=torch.ones(B, L, dtype=torch.bool), n_layer=nl, n_head=H, xattn_n_head=H)
     assert rel_l2(ref.numpy(), y.cpu().numpy()) < TOL
     assert torch.equal(y, yb.transpose(0, 1))
+
+
+def test_postprocess_actions_bit_exact():
+    """scripts/example.py:199-232 (de-discretise, bounds affine, clamp) as one kernel per key vs the oracle: bit-exact."""
+    pol = build_policy("2M")
+    g = torch.Generator().manual_seed(4)
+    B = 37
+    idx = {"pose0_position": torch.stack([torch.randint(0, 50, (1, B), generator=g), torch.randint(0, 100, (1, B), generator=g)], -1),
+           "pose0_rotation": torch.randint(0, 50, (1, B, 4), generator=g),
+           "pose1_position": torch.stack([torch.randint(0, 50, (1, B), generator=g), torch.randint(0, 100, (1, B), generator=g)], -1),
+           "pose1_rotation": torch.randint(0, 50, (1, B, 4), generator=g)}
+    idx["pose0_position"][0, 0] = torch.tensor([49, 99])
+    idx["pose1_position"][0, 0] = torch.tensor([0, 0])
+    low = torch.tensor([[0.25, -0.5]])
+    high = torch.tensor([[0.75, 0.5]])
+    ref = O.postprocess_actions(idx, low, high)
+    got = pol.postprocess_actions({k: v.cuda() for k, v in idx.items()}, low.cuda(), high.cuda())
+    for k in ref:
+        assert got[k].dtype == torch.float32 and got[k].shape == ref[k].shape
+        assert torch.equal(got[k].cpu(), ref[k]), k
+    # one bounds row per episode
+    low_b = low + torch.rand(B, 2, generator=g) * 0.1
+    high_b = high + torch.rand(B, 2, generator=g) * 0.1
+    ref = O.postprocess_actions(idx, low_b[None], high_b[None])
+    got = pol.postprocess_actions({k: v.cuda() for k, v in idx.items()}, low_b.cuda(), high_b.cuda())
+    for k in ref:
+        assert torch.equal(got[k].cpu(), ref[k]), k

@@ -72,6 +72,7 @@ class AttnDesc(C.Structure):
         ("B", c_int), ("H", c_int), ("Lq", c_int), ("Lk", c_int), ("D", c_int),
         ("scale", c_float), ("causal", c_int), ("dtype", c_int),
         ("o_lo8", c_void_p), ("o_hi8", c_void_p), ("ldo8", c_int),
+        ("kv_batch_rows", c_int), ("mask_ld", c_int), ("q_pos0", c_int),
     ]
 
 
@@ -82,8 +83,11 @@ EXPORTS = [
     "vima_split_f32", "vima_pack_weight", "vima_gemm", "vima_glu_block_n", "vima_gemm_f32_grouped", "vima_norm",
     "vima_attention", "vima_small_attention", "vima_assemble_history", "vima_mask_cumsum", "vima_add_pos_embed",
     "vima_gather_prompt", "vima_patchify", "vima_vit_tokens", "vima_bbox_norm", "vima_fill_ee", "vima_max_u8",
-    "vima_action_scale", "vima_head_select", "vima_gato_positions", "vima_pack_weight_f8", "vima_split_f8",
+    "vima_action_scale", "vima_action_postprocess", "vima_object_stats", "vima_crop_resize", "vima_head_select", "vima_gato_positions", "vima_pack_weight_f8", "vima_split_f8",
 ]
+
+
+ABI_VERSION = 3  # include/vima_b200.h VIMA_B200_ABI_VERSION
 
 
 def load_library() -> C.CDLL:
@@ -96,6 +100,10 @@ def load_library() -> C.CDLL:
                 "vima_b200 has no CPU / eager fallback."
             )
         _lib = C.CDLL(LIB_PATH)
+        if _lib.vima_abi_version() != ABI_VERSION:  # descriptor structs below mirror include/vima_b200.h of this version
+            got = _lib.vima_abi_version()
+            _lib = None
+            raise RuntimeError(f"{LIB_PATH} speaks C-ABI v{got}, this package needs v{ABI_VERSION}: rebuild with `python -m vima_b200.build`")
         _lib.vima_last_error.restype = C.c_char_p
         _lib.vima_launch_count.restype = c_i64
         _lib.vima_create.argtypes = [C.POINTER(c_void_p), c_int]
@@ -218,7 +226,8 @@ class Context:
         d.out_lo8, d.out_hi8, d.ld_o8 = _ptr(out_lo8), _ptr(out_hi8), (out_lo8.stride(0) if out_lo8 is not None else 0)
         self._ck(self.lib.vima_norm(self.h, C.byref(d), c_void_p(_stream())), "norm")
 
-    def attention(self, *, q, k, v, o, B, H, Lq, Lk, D, scale, causal=False, key_mask=None, rel_bias=None, dtype=DT_F16, o8=None):
+    def attention(self, *, q, k, v, o, B, H, Lq, Lk, D, scale, causal=False, key_mask=None, rel_bias=None, dtype=DT_F16, o8=None,
+                  kv_batch_rows=0, mask_ld=0, q_pos0=0):
         """q, k, v, o: (hi, lo|None, ld, column offset) tuples over 16-bit operand buffers."""
         es = 2
 
@@ -233,6 +242,7 @@ class Context:
         d.key_mask, d.rel_bias = _ptr(key_mask), _ptr(rel_bias)
         d.B, d.H, d.Lq, d.Lk, d.D = int(B), int(H), int(Lq), int(Lk), int(D)
         d.scale, d.causal, d.dtype = float(scale), int(causal), dtype
+        d.kv_batch_rows, d.mask_ld, d.q_pos0 = int(kv_batch_rows), int(mask_ld), int(q_pos0)
         if o8 is not None:  # (lo8, hi8) uint8 [rows, ld8]
             d.o_lo8, d.o_hi8, d.ldo8 = o8[0].data_ptr(), o8[1].data_ptr(), o8[0].stride(0)
         self._ck(self.lib.vima_attention(self.h, C.byref(d), c_void_p(_stream())), "attention")
@@ -295,6 +305,20 @@ class Context:
     def action_scale(self, idx_i64, n, width, bins, out):
         self._ck(self.lib.vima_action_scale(self.h, c_void_p(idx_i64.data_ptr()), c_i64(n), width, c_void_p(bins.data_ptr()),
                                             c_void_p(out.data_ptr()), c_void_p(_stream())), "action_scale")
+
+    def object_stats(self, segm, n_img, H, W, ids_i64, n_obj, ids_per_image, stats_i32):
+        self._ck(self.lib.vima_object_stats(self.h, c_void_p(segm.data_ptr()), segm.element_size(), n_img, H, W, c_void_p(ids_i64.data_ptr()),
+                                            n_obj, int(ids_per_image), c_void_p(stats_i32.data_ptr()), c_void_p(_stream())), "object_stats")
+
+    def crop_resize(self, rgb_u8, n_img, H, W, stats_i32, n_obj, crops, bbox, mask, n_valid=None):
+        self._ck(self.lib.vima_crop_resize(self.h, c_void_p(rgb_u8.data_ptr()), n_img, H, W, c_void_p(stats_i32.data_ptr()), n_obj,
+                                           c_void_p(crops.data_ptr()), c_void_p(bbox.data_ptr()), c_void_p(mask.data_ptr()),
+                                           c_void_p(_ptr(n_valid)), c_void_p(_stream())), "crop_resize")
+
+    def action_postprocess(self, idx_i64, n, width, bins, lo, hi, bound_stride, out):
+        self._ck(self.lib.vima_action_postprocess(self.h, c_void_p(idx_i64.data_ptr()), c_i64(n), width, c_void_p(bins.data_ptr()),
+                                                  c_void_p(lo.data_ptr()), c_void_p(hi.data_ptr()), bound_stride, c_void_p(out.data_ptr()),
+                                                  c_void_p(_stream())), "action_postprocess")
 
     def head_select(self, logits, B, n_heads, head_off_i32, logits_norm, modes):
         self._ck(self.lib.vima_head_select(self.h, c_void_p(logits.data_ptr()), B, n_heads, c_void_p(head_off_i32.data_ptr()),

@@ -275,6 +275,7 @@ int vima_attention(vima_ctx* c, const vima_attn_desc* d, void* stream) {
   const bool split = d->q_lo != nullptr;
   if (split != (d->k_lo != nullptr) || split != (d->v_lo != nullptr)) return fail(c, VIMA_E_INVALID, "attention: q/k/v lo parts must be all set or all null");
   if (d->rel_bias && d->Lq != d->Lk) return fail(c, VIMA_E_INVALID, "attention: relative bias needs Lq == Lk");
+  if (!(d->scale > 0.f)) return fail(c, VIMA_E_INVALID, "attention: scale must be positive");
   if (d->Lk > 1024) return fail(c, VIMA_E_UNSUPPORTED, "attention: Lk %d exceeds the shared-memory resident design (1024)", d->Lk);
   AttnParams p;
   p.q_hi = (const unsigned short*)d->q_hi; p.q_lo = (const unsigned short*)d->q_lo; p.ldq = d->ldq;
@@ -285,6 +286,9 @@ int vima_attention(vima_ctx* c, const vima_attn_desc* d, void* stream) {
   p.B = d->B; p.H = d->H; p.Lq = d->Lq; p.Lk = d->Lk; p.D = d->D;
   p.scale = d->scale; p.causal = d->causal; p.split = split; p.dtype = d->dtype;
   p.o_lo8 = (unsigned char*)d->o_lo8; p.o_hi8 = (unsigned char*)d->o_hi8; p.ldo8 = d->ldo8;
+  p.kv_batch_rows = d->kv_batch_rows; p.mask_ld = d->mask_ld; p.q_pos0 = d->q_pos0;
+  if ((d->kv_batch_rows && d->kv_batch_rows < d->Lk) || (d->mask_ld && d->mask_ld < d->Lk) || d->q_pos0 < 0)
+    return fail(c, VIMA_E_INVALID, "attention: kv_batch_rows / mask_ld must cover Lk, q_pos0 >= 0");
   if ((p.o_lo8 == nullptr) != (p.o_hi8 == nullptr) || (p.o_lo8 && ((p.ldo8 & 1) || d->dtype != DT_F16)))
     return fail(c, VIMA_E_INVALID, "attention: o_lo8/o_hi8 come together (fp16 format, even ldo8)");
   LAUNCHED(c, launch_attention(p, (cudaStream_t)stream), "attention");
@@ -374,6 +378,33 @@ int vima_max_u8(vima_ctx* c, const uint8_t* x, int64_t n, int* out_max, void* st
 int vima_action_scale(vima_ctx* c, const int64_t* idx, int64_t n, int width, const float* bins_dev, float* out, void* stream) {
   CHECK_CTX(c);
   LAUNCHED(c, launch_action_scale((const long long*)idx, n, width, bins_dev, out, (cudaStream_t)stream), "action_scale");
+}
+
+int vima_object_stats(vima_ctx* c, const void* segm, int segm_elem_bytes, int n_img, int H, int W, const int64_t* obj_ids_dev, int n_obj,
+                      int ids_per_image, int32_t* stats, void* stream) {
+  CHECK_CTX(c);
+  if ((segm_elem_bytes != 1 && segm_elem_bytes != 4 && segm_elem_bytes != 8) || n_obj < 0 || n_obj > 64 || n_img < 0 || H <= 0 || W <= 0)
+    return fail(c, VIMA_E_INVALID, "object_stats: segm elements of 1/4/8 bytes, at most 64 object ids per image");
+  LAUNCHED(c, launch_object_stats(segm, segm_elem_bytes, n_img, H, W, (const long long*)obj_ids_dev, n_obj, ids_per_image, stats,
+                                  (cudaStream_t)stream), "object_stats");
+}
+
+int vima_crop_resize(vima_ctx* c, const uint8_t* rgb, int n_img, int H, int W, const int32_t* stats, int n_obj, uint8_t* crops,
+                     int64_t* bbox, uint8_t* mask, int32_t* n_valid, void* stream) {
+  CHECK_CTX(c);
+  if (n_obj < 0 || n_obj > 64 || n_img < 0 || n_img > 65535 || H <= 0 || W <= 0)
+    return fail(c, VIMA_E_INVALID, "crop_resize: at most 64 object ids per image and 65535 images per call");
+  LAUNCHED(c, launch_crop_resize(rgb, n_img, H, W, stats, n_obj, crops, (long long*)bbox, mask, n_valid, (cudaStream_t)stream),
+           "crop_resize");
+}
+
+int vima_action_postprocess(vima_ctx* c, const int64_t* idx, int64_t n, int width, const float* bins_dev, const float* lo_dev,
+                            const float* hi_dev, int bound_stride, float* out, void* stream) {
+  CHECK_CTX(c);
+  if (width <= 0 || n < 0 || (bound_stride != 0 && bound_stride < width))
+    return fail(c, VIMA_E_INVALID, "action_postprocess: width > 0, n >= 0, bound_stride 0 (broadcast) or >= width");
+  LAUNCHED(c, launch_action_post((const long long*)idx, n, width, bins_dev, lo_dev, hi_dev, bound_stride, out, (cudaStream_t)stream),
+           "action_postprocess");
 }
 
 int vima_head_select(vima_ctx* c, const float* logits, int B, int n_heads, const int32_t* head_off_dev, float* logits_norm, int64_t* modes,

@@ -426,6 +426,27 @@ cudaError_t launch_action_scale(const long long* idx, long long n, int width, co
   return cudaGetLastError();
 }
 
+// The environment-facing step after the heads (scripts/example.py:199-232): de-discretise, affine to the action bounds,
+// clamp: out[i,c] = clamp(idx[i,c]/bins[c] * (hi-lo) + lo, lo, hi) with separately rounded *, + as in torch eager.
+// lo/hi: [rows or 1, width] fp32 (bound_stride 0 broadcasts one row); rotations pass lo=-1, hi=1 (x*2-1, clamp to [-1,1]).
+__global__ void action_post_kernel(const long long* __restrict__ idx, long long n, int width, const float* __restrict__ bins,
+                                   const float* __restrict__ lo, const float* __restrict__ hi, int bound_stride, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * width) return;
+  const int c = (int)(i % width);
+  const long long r = i / width;
+  const float a = (float)idx[i] / __ldg(bins + c);
+  const float l = __ldg(lo + r * bound_stride + c), h = __ldg(hi + r * bound_stride + c);
+  const float y = __fadd_rn(__fmul_rn(a, __fsub_rn(h, l)), l);
+  out[i] = fminf(fmaxf(y, l), h);
+}
+cudaError_t launch_action_post(const long long* idx, long long n, int width, const float* bins, const float* lo, const float* hi,
+                               int bound_stride, float* out, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  action_post_kernel<<<(unsigned)((n * width + 255) / 256), 256, 0, s>>>(idx, n, width, bins, lo, hi, bound_stride, out);
+  return cudaGetLastError();
+}
+
 // Per (episode, head): log-softmax normalised logits (Categorical(logits=...), dists.py:20-23) and the mode
 // = first argmax of the softmax probabilities (dists.py:25-28).  One warp per (b, head).
 __global__ void head_select_kernel(const float* __restrict__ logits, int B, int n_heads, const int* __restrict__ head_off,
