@@ -186,3 +186,25 @@ def gato_state_dict_spec(*, embed_dim: int, n_layer: int, n_head: int = 0, vocab
         sd["t5_prompt_encoder_post_layer.weight"] = (E, 768)
     sd.update(mlp_spec("prompt_obj_post_layer.", [E, 768, 768, 768]))
     return sd
+
+
+def gpt_state_dict_spec(*, embed_dim: int, n_layer: int, n_head: int = 0, vocab_size: int = 40478, n_positions: int = 512):
+    """`VIMAGPTPolicy.state_dict()` of the reference (vima/policy/vima_gpt_policy.py:10-117): the Gato layout with a CLS-token
+    rectangular ViT (9 position rows), a 2E-wide image feature (views concatenated on the feature axis) and therefore a
+    (2E + 2)-wide fusion layer and a 2E-wide prompt object MLP."""
+    E = embed_dim
+    sd = gato_state_dict_spec(embed_dim=embed_dim, n_layer=n_layer, n_head=n_head, vocab_size=vocab_size, n_positions=n_positions)
+    v = "obj_encoder.cropped_img_encoder.vit."
+    out = OrderedDict()
+    for k, shp in sd.items():
+        if k == v + "pos_embed":
+            out[v + "cls_token"] = (768,)
+            out[k] = (9, 768)
+        elif k == "obs_fusion_layer.weight":
+            out[k] = (E, 2 * E + 2)
+        elif k.startswith("prompt_obj_post_layer."):
+            continue
+        else:
+            out[k] = shp
+    out.update(mlp_spec("prompt_obj_post_layer.", [2 * E, 768, 768, 768]))
+    return out

@@ -145,6 +145,10 @@ GATO_CASES = {
 }
 
 
+# VIMA-GPT baseline (one token per observation): same decoder family / image shapes as the Gato cases
+GPT_CASES = {"gpt_small": Case("gpt_small", "gato_tiny", B=2, T=3, n_slots=8, n_words=6, n_imgs=2, ragged=True, seed=31)}
+
+
 def _rgb(tag: str, lead: tuple, seed: int):
     out = {}
     for v in VIEWS:

@@ -547,3 +547,84 @@ def gato_policy_forward(sd: SD, obs_token, action_token, prompt_token, prompt_to
         ids.append(torch.cat([torch.arange(n), torch.full((Lp - n,), n - 1), torch.arange(n, n + L - Lp)]))
     out = hfgpt_forward(sd, "transformer.", tokens, mask, torch.stack(ids).long(), n_head)
     return out[Lp + 1 + Q - 1 :: Q + 1]
+
+
+# ------------------------------------------------------------------------------------------------
+# VIMA-GPT baseline (decoder-only, ONE token per observation / prompt image; vima/policy/vima_gpt_policy.py)
+# ------------------------------------------------------------------------------------------------
+def rect_vit_forward(sd: SD, p: str, img: torch.Tensor, heads: int = 24, patch: int = 32) -> torch.Tensor:
+    """VisionTransformerRectangular.forward, vima/nn/obj_encoder/vit/vit.py:310-330: CLS token + patch tokens, the CLS row
+    after ln_post @ projection is the image feature."""
+    N = img.shape[0]
+    w = sd[p + "conv1.weight"]
+    width = w.shape[0]
+    patches = F.unfold(img, kernel_size=patch, stride=patch).transpose(1, 2)
+    x = _mm(patches, w.reshape(width, -1).t())
+    x = torch.cat([sd[p + "cls_token"].expand(N, 1, width), x], dim=1) + sd[p + "pos_embed"]
+    x = layer_norm(x, sd[p + "ln_pre.weight"], sd[p + "ln_pre.bias"])
+    S = x.shape[1]
+    d = width // heads
+    i = 0
+    while f"{p}blocks.{i}.ln_1.weight" in sd:
+        b = f"{p}blocks.{i}."
+        y = layer_norm(x, sd[b + "ln_1.weight"], sd[b + "ln_1.bias"])
+        q, k, v = linear(y, sd[b + "attn.in_proj_weight"], sd[b + "attn.in_proj_bias"]).split(width, dim=-1)
+        q = q.view(N, S, heads, d).transpose(1, 2)
+        k = k.view(N, S, heads, d).transpose(1, 2)
+        v = v.view(N, S, heads, d).transpose(1, 2)
+        att = torch.softmax(torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(d), dim=-1)
+        o = torch.matmul(att, v).transpose(1, 2).reshape(N, S, width)
+        x = x + linear(o, sd[b + "attn.out_proj.weight"], sd[b + "attn.out_proj.bias"])
+        y = layer_norm(x, sd[b + "ln_2.weight"], sd[b + "ln_2.bias"])
+        h = linear(y, sd[b + "mlp.c_fc.weight"], sd[b + "mlp.c_fc.bias"])
+        h = h * torch.sigmoid(1.702 * h)
+        x = x + linear(h, sd[b + "mlp.c_proj.weight"], sd[b + "mlp.c_proj.bias"])
+        i += 1
+    x = layer_norm(x[:, 0, :], sd[p + "ln_post.weight"], sd[p + "ln_post.bias"])
+    return _mm(x, sd[p + "projection"])
+
+
+def multiview_rgb_encoder(sd: SD, p: str, rgb: dict) -> torch.Tensor:
+    """MultiViewRGBEncoder.forward, vima/nn/obj_encoder/obj_encoder.py:236-242: per-view CLS features concatenated on the
+    FEATURE axis -> (..., 2 * emb_dim)."""
+    outs = []
+    for view in VIEWS:
+        img = rgb[view]
+        lead = img.shape[:-3]
+        f = rect_vit_forward(sd, p + "cropped_img_encoder.vit.", image_preprocess(img).flatten(0, img.dim() - 4))
+        outs.append(f.view(*lead, f.shape[-1]))
+    return torch.cat(outs, dim=-1)
+
+
+def gpt_forward_prompt_assembly(sd: SD, prompts):
+    """VIMAGPTPolicy.forward_prompt_assembly, vima/policy/vima_gpt_policy.py:178-238 (one token per prompt image)."""
+    token_types, word_batch, image_batch = prompts
+    word_emb = sd["prompt_embedding._embed_layer.weight"][word_batch]
+    img_emb = mlp_seq(sd, "prompt_obj_post_layer.", multiview_rgb_encoder(sd, "obj_encoder.", image_batch["rgb"]), (0, 3, 6))
+    B, L_max = len(token_types), max(len(tt) for tt in token_types)
+    toks = torch.zeros(B, L_max, img_emb.shape[-1])
+    masks = torch.zeros(B, L_max, dtype=torch.bool)
+    wp = ip = 0
+    for b, tt in enumerate(token_types):
+        for pos, t in enumerate(tt):
+            if t == 0:
+                toks[b, pos] = word_emb[wp]; wp += 1
+            else:
+                toks[b, pos] = img_emb[ip]; ip += 1
+        masks[b, :len(tt)] = True
+    enc = t5_encoder_forward(sd, "t5_prompt_encoder.t5.encoder.", toks, masks)
+    if "t5_prompt_encoder_post_layer.weight" in sd:
+        enc = linear(enc, sd["t5_prompt_encoder_post_layer.weight"])
+    return enc.transpose(0, 1), masks
+
+
+def gpt_forward_obs_token(sd: SD, obs):
+    """VIMAGPTPolicy.forward_obs_token, vima_gpt_policy.py:240-251 -> (T, B, E)."""
+    img_feats = multiview_rgb_encoder(sd, "obj_encoder.", obs["rgb"])
+    ee_feats = sd["end_effector_encoder.weight"][obs["ee"]]
+    return linear(torch.cat([img_feats, ee_feats], dim=-1), sd["obs_fusion_layer.weight"], sd["obs_fusion_layer.bias"])
+
+
+def gpt_policy_forward(sd: SD, obs_token, action_token, prompt_token, prompt_token_mask, *, n_head: int):
+    """VIMAGPTPolicy.forward, vima_gpt_policy.py:119-176: [prompt | sep | o0 a0 o1 a1 ...], predictions at the obs rows."""
+    return gato_policy_forward(sd, obs_token.unsqueeze(2), action_token, prompt_token, prompt_token_mask, n_head=n_head)

@@ -101,12 +101,17 @@ def run_case(ref_vima, case_name: str):
 
 
 def run_gato_case(ref_vima, case_name: str):
+    """VIMAGatoPolicy (gato_*) or VIMAGPTPolicy (gpt_*): same method chain, one token per observation for the latter."""
     import torch
 
     from oracle import detgen, synth
 
-    case = synth.GATO_CASES[case_name]
-    policy = ref_vima.VIMAGatoPolicy(**synth.GATO_CFGS[case.model]).eval()
+    if case_name.startswith("gpt"):
+        case = synth.GPT_CASES[case_name]
+        policy = sys.modules["vima.policy"].VIMAGPTPolicy(**synth.GATO_CFGS[case.model]).eval()
+    else:
+        case = synth.GATO_CASES[case_name]
+        policy = ref_vima.VIMAGatoPolicy(**synth.GATO_CFGS[case.model]).eval()
     detgen.fill_module_(policy)
     DataDict = sys.modules["vima.utils"].DataDict
     out = {}
@@ -132,7 +137,7 @@ def run_gato_case(ref_vima, case_name: str):
 
 
 def main():
-    names = sys.argv[1:] or (CPU_CASES + ["gato_small"])
+    names = sys.argv[1:] or (CPU_CASES + ["gato_small", "gpt_small"])
     from oracle.ref_shim import load_reference
 
     ref_vima = load_reference()
@@ -141,7 +146,7 @@ def main():
     torch.set_num_threads(os.cpu_count())
     for n in names:
         t0 = time.time()
-        out = run_gato_case(ref_vima, n) if n.startswith("gato") else run_case(ref_vima, n)
+        out = run_gato_case(ref_vima, n) if n.startswith(("gato", "gpt")) else run_case(ref_vima, n)
         path = os.path.join(HERE, f"{n}.npz")
         np.savez_compressed(path, **out)
         print(f"{n}: {len(out)} arrays -> {path} ({os.path.getsize(path)/1e3:.0f} kB) in {time.time()-t0:.1f}s")

@@ -154,3 +154,34 @@ def test_postprocess_actions_bit_exact():
     got = pol.postprocess_actions({k: v.cuda() for k, v in idx.items()}, low_b.cuda(), high_b.cuda())
     for k in ref:
         assert torch.equal(got[k].cpu(), ref[k]), k
+
+
+def test_xattn_gpt_512_prompt_tokens():
+    """north_star allows prompts of up to 512 tokens; the reference's VIMAPolicy caps XAttnGPT at xattn_n_positions=256
+    (vima_policy.py:26-38), so the 512 case exists only at the module level (SURVEY.md 8(d) row #3x): vnn.XAttnGPT built
+    with xattn_n_positions=512 against the oracle's restatement of xattn_gpt.py:73-139."""
+    import vima_b200
+    from oracle import detgen
+    from vima_b200 import nn as vnn
+
+    vima_b200.set_precision("f16x3")
+    E, nl, H, B, L, Lp = 256, 2, 8, 2, 67, 512
+    mod = vnn.XAttnGPT(E, n_layer=nl, n_head=H, dropout=0.1, xattn_n_head=H, xattn_ff_expanding=4, xattn_n_positions=512, use_geglu=True)
+    detgen.fill_module_(mod)
+    sd = {"xattn_gpt." + k: v.detach().clone() for k, v in mod.state_dict().items()}
+    mod = mod.cuda().eval()
+    g = torch.Generator().manual_seed(9)
+    tok = torch.randn(L, B, E, generator=g)
+    ptk = torch.randn(Lp, B, E, generator=g)
+    pmask = torch.ones(B, Lp, dtype=torch.bool)
+    pmask[1, 300:] = False
+    omask = torch.rand(B, L, generator=g) > 0.15
+    omask[:, 0] = True
+    oa_pos = torch.cumsum(omask, dim=1) - 1
+    p_pos = torch.cumsum(pmask, dim=1) - 1
+    with torch.no_grad():
+        ref = O.xattn_gpt_forward(sd, "xattn_gpt.", obs_action_tokens=tok, obs_action_position_ids=oa_pos, prompt_tokens=ptk, prompt_mask=pmask,
+                                  prompt_position_ids=p_pos, obs_action_masks=omask, n_layer=nl, n_head=H, xattn_n_head=H)
+        got = mod(obs_action_tokens=tok.cuda(), obs_action_position_ids=oa_pos.cuda(), prompt_tokens=ptk.cuda(), prompt_mask=pmask.cuda(),
+                  prompt_position_ids=p_pos.cuda(), obs_action_masks=omask.cuda())
+    assert rel_l2(ref, got.cpu()) < 1e-3, rel_l2(ref, got.cpu())

@@ -9,6 +9,7 @@ from .action import (
     MultiCategoricalNet,
 )
 from .basic import Conv1D, Embedding, Linear, MLPSequential, build_mlp
-from .obj_encoder import GatoMultiViewRGBEncoder, GatoViTEncoder, ObjEncoder, ViTEncoder, VisionTransformer
+from .obj_encoder import (GatoMultiViewRGBEncoder, GatoViTEncoder, MultiViewRGBEncoder, ObjEncoder, ViTEncoder, ViTEncoderRectangular,
+                          VisionTransformer)
 from .t5_encoder import T5PromptEncoder, WordEmbedding
 from .xattn_gpt import HFGPT, DecodeCache, XAttnGPT

@@ -72,16 +72,17 @@ def run_vit_blocks(ctx, p, blocks, Wblocks, x32, y16, N, S, Wm, heads):
 
 
 class VisionTransformer(nn.Module):
-    def __init__(self, resolution: int, patch_size: int, width: int, layers: int, heads: int, output_dim: int):
+    def __init__(self, resolution, patch_size: int, width: int, layers: int, heads: int, output_dim: int):
         super().__init__()
-        self._resolution, self._patch_size, self.output_dim = resolution, patch_size, output_dim
+        hw = (resolution, resolution) if isinstance(resolution, int) else tuple(resolution)
+        self._img_hw, self._patch_size, self.output_dim = hw, patch_size, output_dim
         self.width, self.heads = width, heads
         if width // heads != 32:
             raise NotImplementedError("the fused 5-token attention kernel is built for head_dim 32 (all VIMA checkpoints)")
         self.conv1 = nn.Conv2d(3, width, kernel_size=patch_size, stride=patch_size, bias=False)
         scale = width ** -0.5
         self.cls_token = nn.Parameter(scale * torch.randn(width))
-        self.pos_embed = nn.Parameter(scale * torch.randn((resolution // patch_size) ** 2 + 1, width))
+        self.pos_embed = nn.Parameter(scale * torch.randn((hw[0] // patch_size) * (hw[1] // patch_size) + 1, width))
         self.ln_pre = nn.LayerNorm(width)
         self.blocks = nn.Sequential(*[ResidualAttentionBlock(width, heads) for _ in range(layers)])
         self.ln_post = nn.LayerNorm(width)
@@ -103,7 +104,7 @@ class VisionTransformer(nn.Module):
         p = eng.prec()
         N, C, H, Wd = img_u8.shape
         P, Wm = self._patch_size, self.width
-        assert C == 3 and H == self._resolution and Wd == self._resolution
+        assert C == 3 and (H, Wd) == self._img_hw
         dev = img_u8.device
         W = self._packed(ctx, p)
         n_patch = (H // P) * (Wd // P)
@@ -221,6 +222,61 @@ class ObjEncoder(nn.Module):
 # ------------------------------------------------------------------------------------------------------------
 # VIMA-Gato baseline encoder (BASELINE.json configs[4]): whole 64x128 views, 32x32 patches, every patch token kept
 # ------------------------------------------------------------------------------------------------------------
+class VisionTransformerRectangular(VisionTransformer):
+    """vit.py:275-330: the CLS-token ViT on a rectangular image (VIMA-GPT baseline: 64x128, patch 32 -> 1 + 8 tokens)."""
+
+    def __init__(self, img_size, patch_size: int, width: int, layers: int, heads: int, output_dim: int):
+        super().__init__(tuple(img_size), patch_size, width, layers, heads, output_dim)
+
+
+class ViTEncoderRectangular(nn.Module):
+    """vit.py:239-272: (..., 3, H, W) uint8 -> (..., output_dim)."""
+
+    def __init__(self, *, output_dim: int, img_size, patch_size: int, width: int, layers: int, heads: int):
+        super().__init__()
+        self.output_dim = output_dim
+        self.vit = VisionTransformerRectangular(img_size=img_size, patch_size=patch_size, width=width, layers=layers, heads=heads,
+                                                output_dim=output_dim)
+
+    def forward(self, x: torch.Tensor):
+        assert x.dim() >= 4
+        if x.dtype != torch.uint8:
+            x = x.to(torch.uint8)
+        lead = x.shape[:-3]
+        feat16 = self.vit.encode_u8(x.reshape(-1, *x.shape[-3:]))
+        return feat16.float(eng.prec()).view(*lead, self.output_dim)
+
+
+class MultiViewRGBEncoder(nn.Module):
+    """obj_encoder.py:209-246: both views through the shared CLS ViT, features concatenated on the FEATURE axis (2 * emb_dim)."""
+
+    def __init__(self, *, emb_dim: int, views, img_size, vit_patch_size=None, vit_width=None, vit_layers=None, vit_heads=None):
+        super().__init__()
+        self._views = sorted(views)
+        self._transformer_emb_dim = emb_dim
+        self.cropped_img_encoder = ViTEncoderRectangular(img_size=img_size, output_dim=emb_dim, patch_size=vit_patch_size, width=vit_width,
+                                                         layers=vit_layers, heads=vit_heads)
+
+    def encode16(self, rgb, pad_cols: int = 0) -> "eng.Opnd":
+        """rgb {view: (..., 3, H, W) u8} -> 16-bit operands [rows, 2E (+pad)], one batched pass through the shared ViT."""
+        xs = [rgb[v] if rgb[v].dtype == torch.uint8 else rgb[v].to(torch.uint8) for v in self._views]
+        rows = int(xs[0].numel() // (xs[0].shape[-3] * xs[0].shape[-2] * xs[0].shape[-1]))
+        E = self._transformer_emb_dim
+        p = eng.prec()
+        out = eng.Opnd(rows, len(xs) * E + pad_cols, xs[0].device, p.split)
+        for i, x in enumerate(xs):
+            self.cropped_img_encoder.vit.encode_u8(x.reshape(-1, *x.shape[-3:]), out16=out.sub(0, rows, i * E, E))
+        return out
+
+    def forward(self, rgb):
+        lead = rgb[self._views[0]].shape[:-3]
+        return self.encode16(rgb).float(eng.prec()).view(*lead, self.output_dim)
+
+    @property
+    def output_dim(self):
+        return self._transformer_emb_dim * len(self._views)
+
+
 class GatoVisionTransformerRectangular(nn.Module):
     """vit.py:85-134: no CLS token; ln_post and the projection apply to all patch tokens."""
 
