@@ -243,9 +243,16 @@ def ref_attention(q, k, v, scale, causal, key_mask, bias):
     return torch.matmul(torch.softmax(s, -1), v)
 
 
+@pytest.fixture(params=["mma", "tc"])
+def attn_impl(request, monkeypatch):
+    """Both attention kernels: mma.sync (attention.cu) and tcgen05 (attention_tc.cu; shapes it does not take fall back)."""
+    monkeypatch.setenv("VIMA_B200_ATTN", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("split", [False, True])
 @pytest.mark.parametrize("case", ["self32", "cross32", "t5_64", "tiny"])
-def test_attention(ctx, split, case):
+def test_attention(ctx, split, case, attn_impl):
     dt, tdt = DT["f16"]
     g = torch.Generator(device="cuda").manual_seed(3)
     if case == "self32":
@@ -298,7 +305,7 @@ def test_attention(ctx, split, case):
     assert rel(got, ref) < tol, rel(got, ref)
 
 
-def test_attention_fully_masked_prefix(ctx):
+def test_attention_fully_masked_prefix(ctx, attn_impl):
     """Rows whose causally visible keys are all padded follow the reference's -1e4 soft mask exactly."""
     dt, tdt = DT["f16"]
     B, H, L, D = 1, 2, 70, 32
@@ -318,7 +325,7 @@ def test_attention_fully_masked_prefix(ctx):
 
 
 @pytest.mark.parametrize("L0,Ln", [(0, 33), (66, 33), (230, 33), (131, 1)])
-def test_attention_kv_cache_addressing(ctx, L0, Ln):
+def test_attention_kv_cache_addressing(ctx, L0, Ln, attn_impl):
     """Incremental decode: Ln new queries at positions L0.. attend causally over a cache with row pitch Lmax per episode
     (kv_batch_rows / mask_ld / q_pos0); equals the matching rows of the full-history causal attention."""
     dt, tdt = DT["f16"]

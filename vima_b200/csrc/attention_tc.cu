@@ -1,0 +1,340 @@
+// tcgen05 attention for the decoder's hot shapes (head_dim 32, (hi, lo) operand pairs, no relative bias):
+//
+//   one CTA per (batch, head, 128-query-row tile); keys stream through in chunks of 64.
+//   per chunk:  S[128x64]  = Q K^T          6 x tcgen05.mma (M128 N64 K16: hi*hi, lo*hi, hi*lo over head_dim 32), fp32 in TMEM
+//               thread r   = query row r:   tcgen05.ld its 64 scores, log2-domain scale / soft causal / key mask, online
+//                                           max + exp2 + row sum in registers, P -> (hi, lo) fp16 written to shared
+//                                           memory in the 128B-swizzled K-major layout the MMA reads
+//               Oc[128x32] = P V           12 x tcgen05.mma (M128 N32 K16) into a second TMEM region,
+//               o = o * corr + Oc           (running output kept in registers: no TMEM read-modify-write)
+//
+// Same mask semantics as attention.cu (reference components.py:51-80): the causal constant is the reference's soft -1e4,
+// key padding adds finfo.min, rows whose visible keys are all padded keep going past the diagonal.
+// Accumulators live in TMEM, so a thread needs ~100 registers instead of the mma.sync kernel's 128 and three CTAs fit
+// per SM (64 KB of shared memory, 128 TMEM columns each): one CTA's softmax overlaps the others' MMAs and loads.
+#include "kernels.h"
+
+namespace vima {
+
+namespace {
+
+constexpr float FP32_MIN_TC = -3.4028234663852886e38f;
+constexpr float LOG2E_TC = 1.4426950408889634f;
+constexpr float CAUSAL_L2_TC = -1e4f * LOG2E_TC;
+constexpr float EXIT_L2_TC = -9000.f * LOG2E_TC;
+
+constexpr int ATC_THREADS = 160;  // warps 0-3: one query row per thread (TMEM lane = thread); warp 4: MMA issue + TMEM alloc
+constexpr int ATC_BM = 128, ATC_KC = 64, ATC_D = 32;
+constexpr int ATC_TMEM_COLS = 128;  // S: columns [0, 64), O chunk: [64, 96)
+// shared memory carve (bytes, tile bases 1024-aligned)
+constexpr int OFF_QH = 0, OFF_QL = 8192, OFF_KH = 16384, OFF_KL = 20480, OFF_VH = 24576, OFF_VL = 28672, OFF_PH = 32768, OFF_PL = 49152;
+constexpr int OFF_MASK = 65536, OFF_BAR = OFF_MASK + 256, OFF_TPTR = OFF_BAR + 8, ATC_SMEM = OFF_TPTR + 8;
+
+__device__ __forceinline__ uint32_t swz64(uint32_t o) { return o ^ (((o >> 7) & 3u) << 4); }    // 64-byte rows (SWIZZLE_64B)
+__device__ __forceinline__ uint32_t swz128(uint32_t o) { return o ^ (((o >> 7) & 7u) << 4); }   // 128-byte rows (SWIZZLE_128B)
+
+__device__ __forceinline__ uint64_t desc_sw64(uint32_t a) {
+  return (uint64_t)((a >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t a) {
+  return (uint64_t)((a >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// V is consumed as the MN-major B operand of P V: the chunk sits in shared memory exactly as it does in HBM (one 64-byte
+// row of head_dim per key, 64B swizzle) and needs no transpose.  SBO = stride between groups of 8 keys, one K=16 step = 1024 B.
+__device__ __forceinline__ uint64_t desc_sw64_mn(uint32_t a) {
+  return (uint64_t)((a >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc, bool valid) {  // !valid: 16 zero bytes
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(valid ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// rows [r0, r0 + n_rows) of a (hi, lo) operand pair, 64-byte head slices -> two 64B-swizzled tiles; rows >= r_end are zero
+__device__ __forceinline__ void stage_rows(uint32_t s_hi, uint32_t s_lo, const unsigned short* g_hi, const unsigned short* g_lo, size_t row0,
+                                           int ld, int col0, int n_rows, int r_valid, int t, int nt) {
+  for (int idx = t; idx < n_rows * 4; idx += nt) {
+    const int r = idx >> 2, c = idx & 3;
+    const bool ok = r < r_valid;
+    const size_t off = ok ? (row0 + r) * (size_t)ld + col0 + c * 8 : 0;
+    const uint32_t o = swz64((uint32_t)(r * 64 + c * 16));
+    cp_async16(s_hi + o, g_hi + off, ok);
+    cp_async16(s_lo + o, g_lo + off, ok);
+  }
+}
+
+template <int DT>
+__global__ void __launch_bounds__(ATC_THREADS, 3) attention_tc_kernel(const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* sm = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  float* maskadd = reinterpret_cast<float*>(sm + OFF_MASK);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + OFF_BAR);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(sm + OFF_TPTR);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q0 = blockIdx.x * ATC_BM, h = blockIdx.y, b = blockIdx.z;
+  const int Lq = p.Lq, Lk = p.Lk;
+  const int kvb = p.kv_batch_rows ? p.kv_batch_rows : Lk;
+  const int mld = p.mask_ld ? p.mask_ld : Lk;
+  const int qp0 = p.q_pos0;
+  const uint32_t sbase = smem_u32(sm);
+  const int n_chunks = (Lk + ATC_KC - 1) / ATC_KC;
+
+  if (warp == 4) {
+    tmem_alloc<ATC_TMEM_COLS>(tptr);
+    if (lane == 0) {
+      mbar_init(bar, 1);
+      fence_barrier_init();
+    }
+  }
+  // cp.async groups are committed in the order {Q, K0}, {V0}, then per chunk {K(ch+1)}, {V(ch+1)} (possibly empty), so
+  // "wait_group 1" always means: everything except the most recently committed group has landed.
+  // K / V chunk staging: thread t < 128 always copies the same two 16-byte slots (rows t/4 and t/4 + 32, 16-byte column t%4),
+  // so the global offsets and the swizzled shared-memory offsets are computed once.
+  const int ld_r = (tid >> 2) & 31, ld_c = tid & 3;
+  const uint32_t ld_so = swz64((uint32_t)(ld_r * 64 + ld_c * 16));  // row + 32 lands 2048 bytes further (same swizzle phase)
+  const size_t kv_row0 = (size_t)b * kvb + ld_r;
+  const size_t k_off0 = kv_row0 * p.ldk + h * ATC_D + ld_c * 8, v_off0 = kv_row0 * p.ldv + h * ATC_D + ld_c * 8;
+  auto load_chunk = [&](uint32_t s_hi, uint32_t s_lo, const unsigned short* g_hi, const unsigned short* g_lo, size_t off0, int ld, int ch) {
+    if (warp < 4 && ch < n_chunks) {
+      const int rem = Lk - ch * ATC_KC;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const bool ok = ld_r + 32 * i < rem;
+        const size_t off = ok ? off0 + (size_t)(ch * ATC_KC + 32 * i) * ld : 0;
+        cp_async16(s_hi + ld_so + 2048 * i, g_hi + off, ok);
+        cp_async16(s_lo + ld_so + 2048 * i, g_lo + off, ok);
+      }
+    }
+    cp_async_commit();
+  };
+  auto load_k = [&](int ch) { load_chunk(sbase + OFF_KH, sbase + OFF_KL, p.k_hi, p.k_lo, k_off0, p.ldk, ch); };
+  auto load_v = [&](int ch) { load_chunk(sbase + OFF_VH, sbase + OFF_VL, p.v_hi, p.v_lo, v_off0, p.ldv, ch); };
+  if (warp < 4) stage_rows(sbase + OFF_QH, sbase + OFF_QL, p.q_hi, p.q_lo, (size_t)b * Lq + q0, p.ldq, h * ATC_D, ATC_BM, Lq - q0, tid, 128);
+  load_k(0);
+  load_v(0);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tptr;
+  const uint32_t t_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);  // this warp's TMEM lane quadrant (warps 0-3)
+
+  const uint32_t fmt = (DT == DT_BF16) ? 1u : 0u;
+  const uint32_t idesc_s = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(ATC_KC >> 3) << 17) | ((uint32_t)(ATC_BM >> 4) << 24);
+  const uint32_t idesc_o = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 16) | ((uint32_t)(ATC_D >> 3) << 17) | ((uint32_t)(ATC_BM >> 4) << 24);
+
+  const float c_l2 = p.scale * LOG2E_TC;
+  const int row = q0 + tid;  // meaningful for tid < 128
+  // A warp whose 32 query rows all lie past Lq (the 7-row last tile of a 263-token history) only helps with the copies and
+  // barriers: its P rows stay whatever shared memory holds, which only feeds output rows nobody stores.
+  const bool w_on = warp < 4 && (q0 + warp * 32 < Lq);
+  float m_run = -INFINITY, l_run = 0.f;
+  float o_acc[ATC_D];
+#pragma unroll
+  for (int i = 0; i < ATC_D; ++i) o_acc[i] = 0.f;
+  uint32_t phase = 0;
+
+  for (int ch = 0; ch < n_chunks; ++ch) {
+    const int k0 = ch * ATC_KC;
+    // Past the diagonal the tile may stop after this chunk: no prefetch then (a CTA must not exit with copies in flight).
+    const bool may_exit = p.causal && (k0 + ATC_KC > q0 + ATC_BM - 1 + qp0);
+    int masked = 0;
+    if (tid < ATC_KC) {
+      float mk = -INFINITY;  // beyond the sequence: excluded
+      const int j = k0 + tid;
+      if (j < Lk) mk = (p.key_mask == nullptr || p.key_mask[(size_t)b * mld + j]) ? 0.f : FP32_MIN_TC;
+      maskadd[tid] = mk;
+      masked = mk != 0.f;
+    }
+    cp_async_wait<1>();   // K(ch) (and Q) landed; V(ch) may still be in flight
+    fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+    tcgen05_fence_before();
+    const int any_masked = __syncthreads_or(masked);
+    // ---- S = Q K^T ----
+    if (warp == 4 && lane == 0) {
+      tcgen05_fence_after();
+      const uint64_t dqh = desc_sw64(sbase + OFF_QH), dql = desc_sw64(sbase + OFF_QL);
+      const uint64_t dkh = desc_sw64(sbase + OFF_KH), dkl = desc_sw64(sbase + OFF_KL);
+#pragma unroll
+      for (int k = 0; k < ATC_D / 16; ++k) umma_f16(tmem, dqh + 2 * k, dkh + 2 * k, idesc_s, (uint32_t)(k != 0));
+#pragma unroll
+      for (int k = 0; k < ATC_D / 16; ++k) umma_f16(tmem, dql + 2 * k, dkh + 2 * k, idesc_s, 1u);
+#pragma unroll
+      for (int k = 0; k < ATC_D / 16; ++k) umma_f16(tmem, dqh + 2 * k, dkl + 2 * k, idesc_s, 1u);
+      umma_commit(bar);
+    }
+    float corr = 1.f;
+    if (warp < 4) {
+      mbar_wait(bar, phase);
+      phase ^= 1;
+      tcgen05_fence_after();
+      if (!may_exit) load_k(ch + 1); else cp_async_commit();  // the K tile is free once the MMAs above have retired
+    }
+    if (w_on) {
+      uint32_t sv[ATC_KC];
+      tmem_ld_32x32(t_row, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+      tmem_ld_32x32(t_row + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+      tmem_ld_wait();
+      const bool needs_causal = p.causal && (k0 + ATC_KC - 1 > q0 + qp0);
+      float mx = -INFINITY, neg_m;
+      float sc;  // p = exp2(sv * sc - m_new)
+      if (!any_masked && !needs_causal) {  // plain chunk: the scale rides in the exponent FMA
+#pragma unroll
+        for (int c = 0; c < ATC_KC; ++c) mx = fmaxf(mx, __uint_as_float(sv[c]));
+        mx *= c_l2;
+        sc = c_l2;
+      } else {
+        const int thr = row + qp0 - k0;  // key column c of this chunk is causally hidden iff c > thr
+#pragma unroll
+        for (int c4 = 0; c4 < ATC_KC; c4 += 4) {
+          const float4 m4 = *reinterpret_cast<const float4*>(maskadd + c4);
+          const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float y = fmaf(__uint_as_float(sv[c4 + e]), c_l2, mm[e]);
+            if (needs_causal && c4 + e > thr) y = CAUSAL_L2_TC + mm[e];
+            sv[c4 + e] = __float_as_uint(y);
+            mx = fmaxf(mx, y);
+          }
+        }
+        sc = 1.f;
+      }
+      const float m_new = fmaxf(m_run, mx);
+      corr = ex2_approx(m_run - m_new);
+      m_run = m_new;
+      neg_m = -m_new;
+      float ps = 0.f;
+      // P -> (hi, lo) 16-bit pairs, row `tid` of the 128x64 K-major tile (128-byte rows, 128B swizzle)
+#pragma unroll
+      for (int c8 = 0; c8 < ATC_KC / 8; ++c8) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(sv[c8 * 8 + 2 * e]), sc, neg_m));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(sv[c8 * 8 + 2 * e + 1]), sc, neg_m));
+          ps += p0 + p1;
+          split2<DT>(p0, p1, hi[e], lo[e]);
+        }
+        const uint32_t o = swz128((uint32_t)(tid * 128 + c8 * 16));
+        *reinterpret_cast<uint4*>(sm + OFF_PH + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(sm + OFF_PL + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      l_run = l_run * corr + ps;
+    }
+    if (warp < 4) {
+      cp_async_wait<1>();  // V(ch) landed (K(ch+1) may still be in flight)
+      fence_proxy_async();
+      tcgen05_fence_before();
+    }
+    __syncthreads();
+    // ---- O chunk = P V ----
+    if (warp == 4 && lane == 0) {
+      tcgen05_fence_after();
+      const uint64_t dph = desc_sw128(sbase + OFF_PH), dpl = desc_sw128(sbase + OFF_PL);
+      const uint64_t dvh = desc_sw64_mn(sbase + OFF_VH), dvl = desc_sw64_mn(sbase + OFF_VL);
+      const uint32_t t_o = tmem + 64;
+#pragma unroll
+      for (int k = 0; k < ATC_KC / 16; ++k) umma_f16(t_o, dph + 2 * k, dvh + 64 * k, idesc_o, (uint32_t)(k != 0));
+#pragma unroll
+      for (int k = 0; k < ATC_KC / 16; ++k) umma_f16(t_o, dpl + 2 * k, dvh + 64 * k, idesc_o, 1u);
+#pragma unroll
+      for (int k = 0; k < ATC_KC / 16; ++k) umma_f16(t_o, dph + 2 * k, dvl + 64 * k, idesc_o, 1u);
+      umma_commit(bar);
+    }
+    int done = 1;
+    if (warp < 4) {
+      mbar_wait(bar, phase);
+      phase ^= 1;
+      tcgen05_fence_after();
+      if (!may_exit) load_v(ch + 1); else cp_async_commit();  // the V tile is free once P V has retired
+    }
+    if (w_on) {
+      uint32_t ov[ATC_D];
+      tmem_ld_32x32(t_row + 64, ov);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < ATC_D; ++i) o_acc[i] = fmaf(o_acc[i], corr, __uint_as_float(ov[i]));
+      tcgen05_fence_before();
+      done = (row >= Lq) || (m_run > EXIT_L2_TC);
+    }
+    // Every later chunk is causally hidden for all rows of this tile: its weights are exp(-1e4 - m) == 0 in fp32 once
+    // m > -1e4 + 104, so stopping is bit-identical to the reference's full-width softmax (rows that have only seen padded keys
+    // keep going).  Otherwise no barrier is needed here: the two barriers of the next chunk order every reuse.
+    if (may_exit) {
+      if (__syncthreads_and(done)) break;
+      load_k(ch + 1);
+      load_v(ch + 1);
+    }
+  }
+  cp_async_wait<0>();
+
+  // ---- normalise and store (hi, lo) [+ e4m3 views] ----
+  if (warp < 4 && row < Lq) {
+    const float inv = 1.0f / l_run;
+    const size_t off = ((size_t)b * Lq + row) * p.ldo + h * ATC_D;
+#pragma unroll
+    for (int c8 = 0; c8 < ATC_D / 8; ++c8) {
+      uint32_t hi[4], lo[4];
+      float x[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[e] = o_acc[c8 * 8 + e] * inv;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) split2<DT>(x[2 * e], x[2 * e + 1], hi[e], lo[e]);
+      *reinterpret_cast<uint4*>(p.o_hi + off + c8 * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      if (p.o_lo) *reinterpret_cast<uint4*>(p.o_lo + off + c8 * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      if (p.o_lo8) {
+        const size_t off8 = ((size_t)b * Lq + row) * p.ldo8 + h * ATC_D + c8 * 8;
+        uint32_t l8[2], h8[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&hi[2 * e]));
+          const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&hi[2 * e + 1]));
+          l8[e] = e4m3x4((x[4 * e] - f01.x) * F8_ACT_LO_SCALE, (x[4 * e + 1] - f01.y) * F8_ACT_LO_SCALE,
+                         (x[4 * e + 2] - f23.x) * F8_ACT_LO_SCALE, (x[4 * e + 3] - f23.y) * F8_ACT_LO_SCALE);
+          h8[e] = e4m3x4(x[4 * e] * F8_ACT_HI_SCALE, x[4 * e + 1] * F8_ACT_HI_SCALE, x[4 * e + 2] * F8_ACT_HI_SCALE, x[4 * e + 3] * F8_ACT_HI_SCALE);
+        }
+        *reinterpret_cast<uint2*>(p.o_lo8 + off8) = make_uint2(l8[0], l8[1]);
+        *reinterpret_cast<uint2*>(p.o_hi8 + off8) = make_uint2(h8[0], h8[1]);
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tcgen05_fence_after();
+    tmem_dealloc<ATC_TMEM_COLS>(tmem);
+  }
+}
+
+}  // namespace
+
+// Shapes this kernel takes (everything else stays on the mma.sync kernel of attention.cu).
+bool attention_tc_supported(const AttnParams& p) {
+  auto al = [](const void* q) { return ((uintptr_t)q & 15) == 0; };
+  if (!(al(p.q_hi) && al(p.q_lo) && al(p.k_hi) && al(p.k_lo) && al(p.v_hi) && al(p.v_lo) && al(p.o_hi) && al(p.o_lo) && al(p.o_lo8) && al(p.o_hi8)))
+    return false;
+  return p.D == 32 && p.split != 0 && p.rel_bias == nullptr && p.q_lo && p.k_lo && p.v_lo && (p.ldq % 8 == 0) && (p.ldk % 8 == 0) &&
+         (p.ldv % 8 == 0) && (p.ldo % 8 == 0) && (p.o_lo8 == nullptr || p.ldo8 % 8 == 0) && p.H <= 65535 && p.B <= 65535;
+}
+
+cudaError_t launch_attention_tc(const AttnParams& p, cudaStream_t stream) {
+  if (p.B == 0 || p.Lq == 0) return cudaSuccess;
+  dim3 grid((p.Lq + ATC_BM - 1) / ATC_BM, p.H, p.B);
+  const size_t smem = ATC_SMEM + 1024;
+  cudaError_t e;
+  if (p.dtype == DT_BF16) {
+    auto kern = attention_tc_kernel<DT_BF16>;
+    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    kern<<<grid, ATC_THREADS, smem, stream>>>(p);
+  } else {
+    auto kern = attention_tc_kernel<DT_F16>;
+    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    kern<<<grid, ATC_THREADS, smem, stream>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace vima

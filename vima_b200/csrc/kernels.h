@@ -33,6 +33,8 @@ struct AttnParams {
   int q_pos0;                                  // causal: query row i sits at key position q_pos0 + i (incremental decode)
 };
 cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream);
+bool attention_tc_supported(const AttnParams& p);  // tcgen05 variant (attention_tc.cu): head_dim 32, split operands, no bias
+cudaError_t launch_attention_tc(const AttnParams& p, cudaStream_t stream);
 
 struct SmallAttnParams {  // tiny-sequence fp32 attention (ViT: 5 tokens, 24 heads of 32)
   const float* qkv; int ld;        // [N*S, ld], q | k | v each W wide
