@@ -53,9 +53,16 @@ def test_gpt_state_dict_contract():
     assert sorted(sd.keys()) == sorted(spec.keys())
     for k, v in sd.items():
         assert tuple(v.shape) == tuple(spec[k]), k
-    import vima  # the alias package exports it like the reference's vima/policy/__init__.py:1-4
+    # the alias package exports it like the reference's vima/policy/__init__.py:1-4 (checked in a fresh interpreter: other
+    # tests of this session may have put the real reference under the name `vima`)
+    import os
+    import subprocess
+    import sys
 
-    assert vima.policy.VIMAGPTPolicy is vima_b200.VIMAGPTPolicy and hasattr(vima.nn, "MultiViewRGBEncoder")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import vima, vima_b200; assert vima.policy.VIMAGPTPolicy is vima_b200.VIMAGPTPolicy; "
+            "assert hasattr(vima.nn, 'MultiViewRGBEncoder') and hasattr(vima.nn, 'ViTEncoderRectangular')")
+    subprocess.run([sys.executable, "-c", code], cwd=root, check=True, env={**os.environ, "PYTHONPATH": root})
 
 
 @pytest.mark.reference

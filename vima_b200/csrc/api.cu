@@ -291,10 +291,11 @@ int vima_attention(vima_ctx* c, const vima_attn_desc* d, void* stream) {
     return fail(c, VIMA_E_INVALID, "attention: kv_batch_rows / mask_ld must cover Lk, q_pos0 >= 0");
   if ((p.o_lo8 == nullptr) != (p.o_hi8 == nullptr) || (p.o_lo8 && ((p.ldo8 & 1) || d->dtype != DT_F16)))
     return fail(c, VIMA_E_INVALID, "attention: o_lo8/o_hi8 come together (fp16 format, even ldo8)");
-  // VIMA_B200_ATTN = mma | tc | (unset: auto).  The tcgen05 kernel takes head_dim 32, split operands, no bias; auto uses it
-  // when the query tile of 128 rows is reasonably full, the mma.sync kernel otherwise (T5, ViT-sized and decode-step shapes).
+  // VIMA_B200_ATTN = mma (default) | tc.  The tcgen05 kernel (head_dim 32, split operands, no bias) is 10-14 % faster on its own
+  // at the 200M decoder shapes, but inside the power-capped policy step the two are indistinguishable (A/B on one box:
+  // 84.9-85.6 vs 85.7-85.9 ms), so the simpler mma.sync kernel stays the default; both are covered by the kernel tests.
   const char* attn_env = getenv("VIMA_B200_ATTN");
-  const bool want_tc = attn_env ? !strcmp(attn_env, "tc") : (d->Lq >= 96);
+  const bool want_tc = attn_env && !strcmp(attn_env, "tc");
   if (want_tc && attention_tc_supported(p)) { LAUNCHED(c, launch_attention_tc(p, (cudaStream_t)stream), "attention_tc"); }
   LAUNCHED(c, launch_attention(p, (cudaStream_t)stream), "attention");
 }

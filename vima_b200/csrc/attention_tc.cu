@@ -66,6 +66,37 @@ __device__ __forceinline__ void stage_rows(uint32_t s_hi, uint32_t s_lo, const u
   }
 }
 
+// one query row of the output: x = o * inv as (hi, lo) 16-bit pairs [+ e4m3 cross-term views for an "f16f8" consumer GEMM]
+template <int DT>
+__device__ __forceinline__ void store_row(const AttnParams& p, int b, int row, int h, const float (&o)[ATC_D], float inv) {
+  const size_t off = ((size_t)b * p.Lq + row) * p.ldo + h * ATC_D;
+#pragma unroll
+  for (int c8 = 0; c8 < ATC_D / 8; ++c8) {
+    uint32_t hi[4], lo[4];
+    float x[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] = o[c8 * 8 + e] * inv;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) split2<DT>(x[2 * e], x[2 * e + 1], hi[e], lo[e]);
+    *reinterpret_cast<uint4*>(p.o_hi + off + c8 * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    if (p.o_lo) *reinterpret_cast<uint4*>(p.o_lo + off + c8 * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    if (p.o_lo8) {
+      const size_t off8 = ((size_t)b * p.Lq + row) * p.ldo8 + h * ATC_D + c8 * 8;
+      uint32_t l8[2], h8[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&hi[2 * e]));
+        const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&hi[2 * e + 1]));
+        l8[e] = e4m3x4((x[4 * e] - f01.x) * F8_ACT_LO_SCALE, (x[4 * e + 1] - f01.y) * F8_ACT_LO_SCALE,
+                       (x[4 * e + 2] - f23.x) * F8_ACT_LO_SCALE, (x[4 * e + 3] - f23.y) * F8_ACT_LO_SCALE);
+        h8[e] = e4m3x4(x[4 * e] * F8_ACT_HI_SCALE, x[4 * e + 1] * F8_ACT_HI_SCALE, x[4 * e + 2] * F8_ACT_HI_SCALE, x[4 * e + 3] * F8_ACT_HI_SCALE);
+      }
+      *reinterpret_cast<uint2*>(p.o_lo8 + off8) = make_uint2(l8[0], l8[1]);
+      *reinterpret_cast<uint2*>(p.o_hi8 + off8) = make_uint2(h8[0], h8[1]);
+    }
+  }
+}
+
 template <int DT>
 __global__ void __launch_bounds__(ATC_THREADS, 3) attention_tc_kernel(const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -272,35 +303,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 3) attention_tc_kernel(const Attn
   cp_async_wait<0>();
 
   // ---- normalise and store (hi, lo) [+ e4m3 views] ----
-  if (warp < 4 && row < Lq) {
-    const float inv = 1.0f / l_run;
-    const size_t off = ((size_t)b * Lq + row) * p.ldo + h * ATC_D;
-#pragma unroll
-    for (int c8 = 0; c8 < ATC_D / 8; ++c8) {
-      uint32_t hi[4], lo[4];
-      float x[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) x[e] = o_acc[c8 * 8 + e] * inv;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) split2<DT>(x[2 * e], x[2 * e + 1], hi[e], lo[e]);
-      *reinterpret_cast<uint4*>(p.o_hi + off + c8 * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      if (p.o_lo) *reinterpret_cast<uint4*>(p.o_lo + off + c8 * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-      if (p.o_lo8) {
-        const size_t off8 = ((size_t)b * Lq + row) * p.ldo8 + h * ATC_D + c8 * 8;
-        uint32_t l8[2], h8[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&hi[2 * e]));
-          const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&hi[2 * e + 1]));
-          l8[e] = e4m3x4((x[4 * e] - f01.x) * F8_ACT_LO_SCALE, (x[4 * e + 1] - f01.y) * F8_ACT_LO_SCALE,
-                         (x[4 * e + 2] - f23.x) * F8_ACT_LO_SCALE, (x[4 * e + 3] - f23.y) * F8_ACT_LO_SCALE);
-          h8[e] = e4m3x4(x[4 * e] * F8_ACT_HI_SCALE, x[4 * e + 1] * F8_ACT_HI_SCALE, x[4 * e + 2] * F8_ACT_HI_SCALE, x[4 * e + 3] * F8_ACT_HI_SCALE);
-        }
-        *reinterpret_cast<uint2*>(p.o_lo8 + off8) = make_uint2(l8[0], l8[1]);
-        *reinterpret_cast<uint2*>(p.o_hi8 + off8) = make_uint2(h8[0], h8[1]);
-      }
-    }
-  }
+  if (warp < 4 && row < Lq) store_row<DT>(p, b, row, h, o_acc, 1.0f / l_run);
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 4) {
