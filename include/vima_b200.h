@@ -153,6 +153,11 @@ typedef struct {
 } vima_attn_desc;
 int vima_attention(vima_ctx*, const vima_attn_desc* d, void* stream);
 
+/* HF modeling_perceiver.py PerceiverSelfAttention (the resampler of vima/nn/obj_encoder/perceiver/perceiver.py:11-41), fp32:
+ * o[n,i,h*d:(h+1)*d] = softmax_j(q[n,i,h] . k[n,j,h] * scale) v[n,j,h]; Lk <= 16, d <= 128; q_batch_stride 0 shares the queries
+ * (the learned latents of the cross-attention layer) between all N images. */
+int vima_latent_attention(vima_ctx*, const float* q, int ldq, int64_t q_batch_stride, const float* k, int ldk, const float* v, int ldv, float* o,
+                          int ldo, int64_t N, int Lq, int Lk, int H, int d, float scale, void* stream);
 /* nn.MultiheadAttention core on tiny sequences (ViT, vit.py:203,224-230): fp32 qkv [N*S, ld] (q|k|v, W wide each,
  * bias included) -> (hi, lo) [N*S, ldo].  head_dim must be 32, S <= 16. */
 int vima_small_attention(vima_ctx*, const float* qkv, int ld, int64_t N, int S, int H, int W, float scale, void* o_hi, void* o_lo,

@@ -122,6 +122,10 @@ def load_reference():
 
     if not hasattr(VIMAGPTPolicy, "device"):  # same missing attribute (vima_gpt_policy.py:131)
         VIMAGPTPolicy.device = property(lambda s: next(s.parameters()).device)
+    from vima.policy.vima_flamingo_policy import VIMAFlamingoPolicy
+
+    if not hasattr(VIMAFlamingoPolicy, "device"):  # vima_flamingo_policy.py:141
+        VIMAFlamingoPolicy.device = property(lambda s: next(s.parameters()).device)
 
     assert ref_vima.__file__.startswith(REFERENCE_ROOT), ref_vima.__file__
     _loaded = ref_vima

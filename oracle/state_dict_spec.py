@@ -208,3 +208,46 @@ def gpt_state_dict_spec(*, embed_dim: int, n_layer: int, n_head: int = 0, vocab_
             out[k] = shp
     out.update(mlp_spec("prompt_obj_post_layer.", [2 * E, 768, 768, 768]))
     return out
+
+
+def perceiver_spec(p: str, E: int, *, num_latents: int = 4, n_self: int = 4):
+    """HF PerceiverModel keys as ObjectsPerceiverEncoder holds them (perceiver.py:25-38; widening factors 1, qk/v channels = E)."""
+    sd = OrderedDict()
+    sd[p + "model.embeddings.latents"] = (num_latents, E)
+
+    def layer(q: str, cross: bool):
+        a = q + "attention.self."
+        for ln in ("layernorm1",) + (("layernorm2",) if cross else ()):
+            sd[a + ln + ".weight"] = (E,)
+            sd[a + ln + ".bias"] = (E,)
+        for lin in ("query", "key", "value"):
+            sd[a + lin + ".weight"] = (E, E)
+            sd[a + lin + ".bias"] = (E,)
+        for lin in ("attention.output.dense", "mlp.dense1", "mlp.dense2"):
+            sd[q + lin + ".weight"] = (E, E)
+            sd[q + lin + ".bias"] = (E,)
+        sd[q + "layernorm.weight"] = (E,)
+        sd[q + "layernorm.bias"] = (E,)
+
+    layer(p + "model.encoder.cross_attention.", True)
+    for i in range(n_self):
+        layer(f"{p}model.encoder.self_attends.{i}.", False)
+    return sd
+
+
+def flamingo_state_dict_spec(*, embed_dim: int, dt_n_layers: int, dt_n_heads: int = 0, xattn_n_heads: int = 0):
+    """`VIMAFlamingoPolicy.state_dict()` of the reference (vima/policy/vima_flamingo_policy.py:10-127): the XAttnGPT decoder of
+    VIMAPolicy, the Gato ViT + HF Perceiver resampler as object encoder (sub-module spelled `peceiver`), Gato-style heads."""
+    E = embed_dim
+    sd = OrderedDict()
+    sd.update(xattn_gpt_spec("xattn_gpt.", E, dt_n_layers))
+    g = gato_state_dict_spec(embed_dim=E, n_layer=0)
+    for k, shp in g.items():
+        if k.startswith("obj_encoder."):
+            sd[k] = shp
+    sd.update(perceiver_spec("obj_encoder.peceiver.", E))
+    for k, shp in g.items():
+        if k.startswith(("end_effector_encoder", "obs_fusion_layer", "action_encoder", "action_decoder", "prompt_embedding", "t5_prompt_encoder",
+                         "prompt_obj_post_layer")):
+            sd[k] = shp
+    return sd

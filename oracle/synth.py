@@ -149,6 +149,11 @@ GATO_CASES = {
 GPT_CASES = {"gpt_small": Case("gpt_small", "gato_tiny", B=2, T=3, n_slots=8, n_words=6, n_imgs=2, ragged=True, seed=31)}
 
 
+# VIMA-Flamingo baseline: XAttnGPT decoder + Perceiver-resampled image tokens (4 per image)
+FLAMINGO_CFGS = {"flamingo_tiny": dict(embed_dim=256, dt_n_layers=2, dt_n_heads=8, xattn_n_heads=8)}
+FLAMINGO_CASES = {"flamingo_small": Case("flamingo_small", "flamingo_tiny", B=2, T=2, n_slots=8, n_words=6, n_imgs=2, ragged=True, seed=41)}
+
+
 def _rgb(tag: str, lead: tuple, seed: int):
     out = {}
     for v in VIEWS:

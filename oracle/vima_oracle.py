@@ -628,3 +628,100 @@ def gpt_forward_obs_token(sd: SD, obs):
 def gpt_policy_forward(sd: SD, obs_token, action_token, prompt_token, prompt_token_mask, *, n_head: int):
     """VIMAGPTPolicy.forward, vima_gpt_policy.py:119-176: [prompt | sep | o0 a0 o1 a1 ...], predictions at the obs rows."""
     return gato_policy_forward(sd, obs_token.unsqueeze(2), action_token, prompt_token, prompt_token_mask, n_head=n_head)
+
+
+# ------------------------------------------------------------------------------------------------
+# VIMA-Flamingo baseline: XAttnGPT decoder over Perceiver-resampled image tokens (vima/policy/vima_flamingo_policy.py)
+# ------------------------------------------------------------------------------------------------
+def _perceiver_layer(sd: SD, p: str, x: torch.Tensor, inputs: Optional[torch.Tensor], heads: int) -> torch.Tensor:
+    """HF:modeling_perceiver.py PerceiverLayer.forward (PerceiverSelfAttention + PerceiverSelfOutput + query residual, then
+    LayerNorm -> dense1 -> GELU -> dense2 + residual).  x (N,Lq,E) latents; inputs (N,Lk,E) for the cross-attention layer."""
+    a = p + "attention.self."
+    h = layer_norm(x, sd[a + "layernorm1.weight"], sd[a + "layernorm1.bias"])
+    kv = h
+    if inputs is not None:
+        kv = layer_norm(inputs, sd[a + "layernorm2.weight"], sd[a + "layernorm2.bias"])
+    q = linear(h, sd[a + "query.weight"], sd[a + "query.bias"])
+    k = linear(kv, sd[a + "key.weight"], sd[a + "key.bias"])
+    v = linear(kv, sd[a + "value.weight"], sd[a + "value.bias"])
+    N, Lq, E = q.shape
+    Lk, d = k.shape[1], E // heads
+    q = q.view(N, Lq, heads, d).transpose(1, 2)
+    k = k.view(N, Lk, heads, d).transpose(1, 2)
+    v = v.view(N, Lk, heads, d).transpose(1, 2)
+    att = torch.softmax(torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(d), dim=-1)  # inputs mask is all ones (obj_encoder.py:199-203)
+    ctx = torch.matmul(att, v).transpose(1, 2).reshape(N, Lq, E)
+    x = linear(ctx, sd[p + "attention.output.dense.weight"], sd[p + "attention.output.dense.bias"]) + x  # use_query_residual
+    h = layer_norm(x, sd[p + "layernorm.weight"], sd[p + "layernorm.bias"])
+    h = F.gelu(linear(h, sd[p + "mlp.dense1.weight"], sd[p + "mlp.dense1.bias"]))
+    return linear(h, sd[p + "mlp.dense2.weight"], sd[p + "mlp.dense2.bias"]) + x
+
+
+def perceiver_forward(sd: SD, p: str, inputs: torch.Tensor, *, num_blocks: int = 4, heads: int = 8) -> torch.Tensor:
+    """ObjectsPerceiverEncoder.forward = HF PerceiverModel(inputs, all-ones mask).last_hidden_state
+    (vima/nn/obj_encoder/perceiver/perceiver.py:11-41; HF PerceiverEncoder.forward: one cross-attention layer, then the SAME
+    stack of self-attention layers applied `num_blocks` times).  inputs (N,L,E) -> (N,num_latents,E)."""
+    x = sd[p + "model.embeddings.latents"].expand(inputs.shape[0], -1, -1)
+    x = _perceiver_layer(sd, p + "model.encoder.cross_attention.", x, inputs, heads)
+    n_self = 0
+    while f"{p}model.encoder.self_attends.{n_self}.layernorm.weight" in sd:
+        n_self += 1
+    for _ in range(num_blocks):
+        for i in range(n_self):
+            x = _perceiver_layer(sd, f"{p}model.encoder.self_attends.{i}.", x, None, heads)
+    return x
+
+
+def perceiver_obj_encoder(sd: SD, p: str, rgb: dict) -> torch.Tensor:
+    """MultiViewRGBPerceiverEncoder.forward, vima/nn/obj_encoder/obj_encoder.py:192-205: Gato ViT patch tokens of both views
+    (16 per image) resampled to 4 latent tokens.  (The reference spells the sub-module `peceiver`.)"""
+    feats = gato_obj_encoder(sd, p, rgb)  # (..., 16, E)
+    lead = feats.shape[:-2]
+    out = perceiver_forward(sd, p + "peceiver.", feats.reshape(-1, *feats.shape[-2:]))
+    return out.view(*lead, *out.shape[-2:])
+
+
+def flamingo_forward_prompt_assembly(sd: SD, prompts):
+    """VIMAFlamingoPolicy.forward_prompt_assembly, vima_flamingo_policy.py:165-228 (4 tokens per prompt image)."""
+    token_types, word_batch, image_batch = prompts
+    word_emb = sd["prompt_embedding._embed_layer.weight"][word_batch]
+    img_emb = mlp_seq(sd, "prompt_obj_post_layer.", perceiver_obj_encoder(sd, "obj_encoder.", image_batch["rgb"]), (0, 3, 6))
+    nq = img_emb.shape[-2]
+    lens = [sum(1 if t == 0 else nq for t in tt) for tt in token_types]
+    B, L_max = len(token_types), max(lens)
+    toks = torch.zeros(B, L_max, img_emb.shape[-1])
+    masks = torch.zeros(B, L_max, dtype=torch.bool)
+    wp = ip = 0
+    for b, tt in enumerate(token_types):
+        pos = 0
+        for t in tt:
+            if t == 0:
+                toks[b, pos] = word_emb[wp]; wp += 1; pos += 1
+            else:
+                toks[b, pos:pos + nq] = img_emb[ip]; ip += 1; pos += nq
+        masks[b, :pos] = True
+    enc = t5_encoder_forward(sd, "t5_prompt_encoder.t5.encoder.", toks, masks)
+    if "t5_prompt_encoder_post_layer.weight" in sd:
+        enc = linear(enc, sd["t5_prompt_encoder_post_layer.weight"])
+    return enc.transpose(0, 1), masks
+
+
+def flamingo_forward_obs_token(sd: SD, obs):
+    """VIMAFlamingoPolicy.forward_obs_token, vima_flamingo_policy.py:230-240 -> (T, B, 4, E)."""
+    img_feats = perceiver_obj_encoder(sd, "obj_encoder.", obs["rgb"])
+    ee_feats = sd["end_effector_encoder.weight"][obs["ee"]].unsqueeze(2).repeat(1, 1, img_feats.shape[-2], 1)
+    return linear(torch.cat([img_feats, ee_feats], dim=-1), sd["obs_fusion_layer.weight"], sd["obs_fusion_layer.bias"])
+
+
+def flamingo_policy_forward(sd: SD, obs_token, action_token, prompt_token, prompt_token_mask, *, n_head: int, xattn_n_head: int):
+    """VIMAFlamingoPolicy.forward, vima_flamingo_policy.py:129-163: the VIMA history layout with every token valid and DEFAULT
+    position ids (arange over the history and over the padded prompt; no cumsum of masks here)."""
+    T, B, Q, E = obs_token.shape
+    E2, n_layer = policy_dims(sd)
+    tokens, masks, _ = assemble_history(obs_token, torch.ones(T, B, Q, dtype=torch.bool), action_token)
+    L, Lp = tokens.shape[0], prompt_token.shape[0]
+    out = xattn_gpt_forward(
+        sd, "xattn_gpt.", obs_action_tokens=tokens, obs_action_position_ids=torch.arange(L).expand(B, L), prompt_tokens=prompt_token,
+        prompt_mask=prompt_token_mask, prompt_position_ids=torch.arange(Lp).expand(B, Lp), obs_action_masks=masks.transpose(0, 1),
+        n_layer=n_layer, n_head=n_head, xattn_n_head=xattn_n_head)
+    return out[Q - 1 :: Q + 1]

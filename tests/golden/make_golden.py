@@ -106,7 +106,10 @@ def run_gato_case(ref_vima, case_name: str):
 
     from oracle import detgen, synth
 
-    if case_name.startswith("gpt"):
+    if case_name.startswith("flamingo"):
+        case = synth.FLAMINGO_CASES[case_name]
+        policy = sys.modules["vima.policy"].VIMAFlamingoPolicy(**synth.FLAMINGO_CFGS[case.model]).eval()
+    elif case_name.startswith("gpt"):
         case = synth.GPT_CASES[case_name]
         policy = sys.modules["vima.policy"].VIMAGPTPolicy(**synth.GATO_CFGS[case.model]).eval()
     else:
@@ -137,7 +140,7 @@ def run_gato_case(ref_vima, case_name: str):
 
 
 def main():
-    names = sys.argv[1:] or (CPU_CASES + ["gato_small", "gpt_small"])
+    names = sys.argv[1:] or (CPU_CASES + ["gato_small", "gpt_small", "flamingo_small"])
     from oracle.ref_shim import load_reference
 
     ref_vima = load_reference()
@@ -146,7 +149,7 @@ def main():
     torch.set_num_threads(os.cpu_count())
     for n in names:
         t0 = time.time()
-        out = run_gato_case(ref_vima, n) if n.startswith(("gato", "gpt")) else run_case(ref_vima, n)
+        out = run_gato_case(ref_vima, n) if n.startswith(("gato", "gpt", "flamingo")) else run_case(ref_vima, n)
         path = os.path.join(HERE, f"{n}.npz")
         np.savez_compressed(path, **out)
         print(f"{n}: {len(out)} arrays -> {path} ({os.path.getsize(path)/1e3:.0f} kB) in {time.time()-t0:.1f}s")

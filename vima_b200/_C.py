@@ -83,7 +83,7 @@ EXPORTS = [
     "vima_split_f32", "vima_pack_weight", "vima_gemm", "vima_glu_block_n", "vima_gemm_f32_grouped", "vima_norm",
     "vima_attention", "vima_small_attention", "vima_assemble_history", "vima_mask_cumsum", "vima_add_pos_embed",
     "vima_gather_prompt", "vima_patchify", "vima_vit_tokens", "vima_bbox_norm", "vima_fill_ee", "vima_max_u8",
-    "vima_action_scale", "vima_action_postprocess", "vima_object_stats", "vima_crop_resize", "vima_head_select", "vima_gato_positions", "vima_pack_weight_f8", "vima_split_f8",
+    "vima_action_scale", "vima_action_postprocess", "vima_latent_attention", "vima_object_stats", "vima_crop_resize", "vima_head_select", "vima_gato_positions", "vima_pack_weight_f8", "vima_split_f8",
 ]
 
 
@@ -314,6 +314,11 @@ class Context:
         self._ck(self.lib.vima_crop_resize(self.h, c_void_p(rgb_u8.data_ptr()), n_img, H, W, c_void_p(stats_i32.data_ptr()), n_obj,
                                            c_void_p(crops.data_ptr()), c_void_p(bbox.data_ptr()), c_void_p(mask.data_ptr()),
                                            c_void_p(_ptr(n_valid)), c_void_p(_stream())), "crop_resize")
+
+    def latent_attention(self, *, q, ldq, q_batch_stride, k, ldk, v, ldv, o, ldo, N, Lq, Lk, H, d, scale):
+        self._ck(self.lib.vima_latent_attention(self.h, c_void_p(q.data_ptr()), ldq, c_i64(q_batch_stride), c_void_p(k.data_ptr()), ldk,
+                                                c_void_p(v.data_ptr()), ldv, c_void_p(o.data_ptr()), ldo, c_i64(N), Lq, Lk, H, d,
+                                                C.c_float(scale), c_void_p(_stream())), "latent_attention")
 
     def action_postprocess(self, idx_i64, n, width, bins, lo, hi, bound_stride, out):
         self._ck(self.lib.vima_action_postprocess(self.h, c_void_p(idx_i64.data_ptr()), c_i64(n), width, c_void_p(bins.data_ptr()),

@@ -4,9 +4,9 @@ import os
 import torch
 
 from .engine import get_precision, set_precision
-from .policy import VIMAGatoPolicy, VIMAGPTPolicy, VIMAPolicy
+from .policy import VIMAFlamingoPolicy, VIMAGatoPolicy, VIMAGPTPolicy, VIMAPolicy
 
-__all__ = ["VIMAPolicy", "VIMAGatoPolicy", "VIMAGPTPolicy", "create_policy_from_ckpt", "set_precision", "get_precision"]
+__all__ = ["VIMAPolicy", "VIMAGatoPolicy", "VIMAGPTPolicy", "VIMAFlamingoPolicy", "create_policy_from_ckpt", "set_precision", "get_precision"]
 
 
 def create_policy_from_ckpt(ckpt_path, device):

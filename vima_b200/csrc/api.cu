@@ -300,6 +300,18 @@ int vima_attention(vima_ctx* c, const vima_attn_desc* d, void* stream) {
   LAUNCHED(c, launch_attention(p, (cudaStream_t)stream), "attention");
 }
 
+int vima_latent_attention(vima_ctx* c, const float* q, int ldq, int64_t q_batch_stride, const float* k, int ldk, const float* v, int ldv, float* o,
+                          int ldo, int64_t N, int Lq, int Lk, int H, int d, float scale, void* stream) {
+  CHECK_CTX(c);
+  if (!q || !k || !v || !o) return fail(c, VIMA_E_INVALID, "latent_attention: null pointer");
+  if (Lk < 1 || Lk > 16 || d < 1 || d > 128 || Lq < 0 || N < 0 || H < 1)
+    return fail(c, VIMA_E_UNSUPPORTED, "latent_attention: 1..16 keys, head_dim <= 128 (Lk %d, d %d)", Lk, d);
+  LatentAttnParams p;
+  p.q = q; p.ldq = ldq; p.q_batch_stride = q_batch_stride; p.k = k; p.ldk = ldk; p.v = v; p.ldv = ldv; p.o = o; p.ldo = ldo;
+  p.N = N; p.Lq = Lq; p.Lk = Lk; p.H = H; p.d = d; p.scale = scale;
+  LAUNCHED(c, launch_latent_attention(p, (cudaStream_t)stream), "latent_attention");
+}
+
 int vima_small_attention(vima_ctx* c, const float* qkv, int ld, int64_t N, int S, int H, int W, float scale, void* o_hi, void* o_lo, int ldo,
                          float* o_f32, int dtype, void* stream) {
   CHECK_CTX(c);

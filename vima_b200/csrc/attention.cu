@@ -401,4 +401,65 @@ cudaError_t launch_small_attention(const SmallAttnParams& p, cudaStream_t stream
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Latent attention in fp32 (HF Perceiver resampler of the VIMA-Flamingo baseline, modeling_perceiver.py PerceiverSelfAttention):
+// a handful of latent queries against <= 16 keys, head_dim <= 128.  One warp per (image, head); lane l owns head
+// dimensions l, l+32, l+64, l+96.  q may be shared by all images (q_batch_stride 0: the cross-attention queries are the
+// learned latents).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int LAT_LK_MAX = 16, LAT_DV = 4;
+
+__global__ void __launch_bounds__(256) latent_attention_kernel(const LatentAttnParams p) {
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= p.N * p.H) return;
+  const long long n = w / p.H;
+  const int h = (int)(w % p.H);
+  const int d = p.d;
+  const float* qb = p.q + (size_t)n * p.q_batch_stride + h * d;
+  const float* kb = p.k + (size_t)n * p.Lk * p.ldk + h * d;
+  const float* vb = p.v + (size_t)n * p.Lk * p.ldv + h * d;
+  for (int i = 0; i < p.Lq; ++i) {
+    float qv[LAT_DV];
+#pragma unroll
+    for (int e = 0; e < LAT_DV; ++e) qv[e] = (lane + 32 * e < d) ? __ldg(qb + (size_t)i * p.ldq + lane + 32 * e) : 0.f;
+    float sc[LAT_LK_MAX];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < LAT_LK_MAX; ++j) {
+      if (j < p.Lk) {
+        float part = 0.f;
+#pragma unroll
+        for (int e = 0; e < LAT_DV; ++e)
+          if (lane + 32 * e < d) part = fmaf(qv[e], __ldg(kb + (size_t)j * p.ldk + lane + 32 * e), part);
+        sc[j] = warp_sum(part) * p.scale;
+        mx = fmaxf(mx, sc[j]);
+      }
+    }
+    float den = 0.f, acc[LAT_DV] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < LAT_LK_MAX; ++j) {
+      if (j < p.Lk) {
+        const float e_ = expf(sc[j] - mx);
+        den += e_;
+#pragma unroll
+        for (int e = 0; e < LAT_DV; ++e)
+          if (lane + 32 * e < d) acc[e] = fmaf(e_, __ldg(vb + (size_t)j * p.ldv + lane + 32 * e), acc[e]);
+      }
+    }
+    const float inv = 1.0f / den;
+#pragma unroll
+    for (int e = 0; e < LAT_DV; ++e)
+      if (lane + 32 * e < d) p.o[((size_t)n * p.Lq + i) * p.ldo + h * d + lane + 32 * e] = acc[e] * inv;
+  }
+}
+
+cudaError_t launch_latent_attention(const LatentAttnParams& p, cudaStream_t stream) {
+  if (p.N == 0 || p.Lq == 0) return cudaSuccess;
+  if (p.Lk > LAT_LK_MAX || p.Lk < 1 || p.d > 32 * LAT_DV || p.d < 1) return cudaErrorInvalidValue;
+  const long long warps = p.N * p.H;
+  latent_attention_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
 }  // namespace vima

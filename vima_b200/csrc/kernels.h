@@ -43,6 +43,15 @@ struct SmallAttnParams {  // tiny-sequence fp32 attention (ViT: 5 tokens, 24 hea
 };
 cudaError_t launch_small_attention(const SmallAttnParams& p, cudaStream_t stream);
 
+struct LatentAttnParams {  // fp32 attention of a few latent queries over <= 16 keys (Perceiver resampler)
+  const float* q; int ldq; long long q_batch_stride;  // [N or 1][Lq, ldq]; stride 0 = the same queries for every image
+  const float* k; int ldk;                            // [N*Lk, ldk]
+  const float* v; int ldv;
+  float* o; int ldo;                                  // [N*Lq, ldo]
+  long long N; int Lq, Lk, H, d; float scale;
+};
+cudaError_t launch_latent_attention(const LatentAttnParams& p, cudaStream_t stream);
+
 struct SimtGemmGroup {  // one fp32 problem: y[M, n] = act(x[M, k] * w[n, k]^T + b)
   const float* x; int ldx;
   const float* w; int ldw;

@@ -9,7 +9,8 @@ from .action import (
     MultiCategoricalNet,
 )
 from .basic import Conv1D, Embedding, Linear, MLPSequential, build_mlp
-from .obj_encoder import (GatoMultiViewRGBEncoder, GatoViTEncoder, MultiViewRGBEncoder, ObjEncoder, ViTEncoder, ViTEncoderRectangular,
+from .obj_encoder import (GatoMultiViewRGBEncoder, GatoViTEncoder, MultiViewRGBEncoder, MultiViewRGBPerceiverEncoder, ObjEncoder, ViTEncoder, ViTEncoderRectangular,
                           VisionTransformer)
+from .perceiver import ObjectsPerceiverEncoder
 from .t5_encoder import T5PromptEncoder, WordEmbedding
 from .xattn_gpt import HFGPT, DecodeCache, XAttnGPT

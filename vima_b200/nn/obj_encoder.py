@@ -340,6 +340,42 @@ class GatoViTEncoder(nn.Module):
         return out.view(*lead, *out.shape[-2:])
 
 
+class MultiViewRGBPerceiverEncoder(nn.Module):
+    """obj_encoder.py:150-206: the Gato ViT's patch tokens of both views (16 per image) resampled by the Perceiver to
+    `perceiver_num_queries` tokens.  The reference spells the sub-module `peceiver`; the state-dict keys keep that spelling."""
+
+    def __init__(self, *, emb_dim: int, views, img_size, vit_patch_size=None, vit_width=None, vit_layers=None, vit_heads=None,
+                 perceiver_num_queries: int, perceiver_num_blocks: int, perceiver_num_self_attends_per_block: int,
+                 perceiver_num_self_attention_heads: int, perceiver_num_cross_attention_heads: int, perceiver_attention_probs_dropout_prob: float):
+        super().__init__()
+        from .perceiver import ObjectsPerceiverEncoder
+
+        self._views = sorted(views)
+        self._transformer_emb_dim = emb_dim
+        self.cropped_img_encoder = GatoViTEncoder(img_size=img_size, output_dim=emb_dim, patch_size=vit_patch_size, width=vit_width,
+                                                  layers=vit_layers, heads=vit_heads)
+        self.peceiver = ObjectsPerceiverEncoder(emb_dim, num_latents=perceiver_num_queries, num_blocks=perceiver_num_blocks,
+                                                num_self_attends_per_block=perceiver_num_self_attends_per_block,
+                                                num_self_attention_heads=perceiver_num_self_attention_heads,
+                                                num_cross_attention_heads=perceiver_num_cross_attention_heads,
+                                                attention_probs_dropout_prob=perceiver_attention_probs_dropout_prob)
+
+    def forward(self, rgb):
+        views = self._views
+        xs = [rgb[v] if rgb[v].dtype == torch.uint8 else rgb[v].to(torch.uint8) for v in views]
+        lead = xs[0].shape[:-3]
+        n = int(xs[0].numel() // (xs[0].shape[-3] * xs[0].shape[-2] * xs[0].shape[-1]))
+        allx = torch.cat([x.reshape(-1, *x.shape[-3:]) for x in xs], dim=0)  # one batched pass through the shared ViT
+        feats = self.cropped_img_encoder.vit.encode_u8(allx)  # (n_views * n, L, E)
+        tokens = torch.cat([feats[i * n:(i + 1) * n] for i in range(len(views))], dim=1)  # (n, n_views * L, E)
+        out = self.peceiver(tokens, torch.ones(tokens.shape[:2], dtype=torch.bool, device=tokens.device))
+        return out.view(*lead, *out.shape[-2:])
+
+    @property
+    def output_dim(self):
+        return self._transformer_emb_dim
+
+
 class GatoMultiViewRGBEncoder(nn.Module):
     """obj_encoder.py:102-147: both views through the shared Gato ViT, patch tokens concatenated on the token axis."""
 
