@@ -1,19 +1,30 @@
 #!/usr/bin/env python
 """bench.py -- policy steps/sec of the VIMA policy forward pass on B200 (contract: see the task statement).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg3] [--precision f16x3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg3|cfg2|cfg3x|cfg5]
+                    [--precision f16f8] [--ragged] [--graph]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
 One "step" = one policy step for every episode of the batch, exactly as scripts/example.py chains the policy's
 public methods with a full-history re-forward:
     forward_obs_token(new obs) -> forward(T obs steps, T-1 actions, prompt) -> forward_action_decoder(last row)
     -> .mode() -> forward_action_token(action)                       [prompt encode is once per episode: untimed, reported]
-Workload = BASELINE.json configs[2]: VIMA-200M, 256 episodes per GPU, Q=32 object tokens, Lp=256, T=8 (L=263).
-`value`   : device-timed (CUDA events), inputs resident in HBM.
-`e2e`     : same step through the same public methods but the new observation comes from pinned HOST memory
-            (H2D inside the timed region) and the action indices are read back to the host every step.
-`--impl reference`: the CPU oracle port of the reference (oracle/vima_oracle.py, torch fp32, all host threads)
-            on a bounded sample of the same workload.
+
+Workloads (BASELINE.json configs / SURVEY.md 8(d) rows):
+    cfg3  (default, the headline)  VIMA-200M, 256 episodes/GPU, Q=32, Lp=256, T=8 (L=263)           configs[2] / row #3
+    cfg2                            VIMA-20M, 64 episodes/GPU, Q=16, Lp=64, T=4 (L=67)               configs[1] / row #2
+    cfg3x                           cfg3 with a 512-token prompt through XAttnGPT(xattn_n_positions=512) -- beyond the
+                                    reference VIMAPolicy's cap (vima_policy.py:26-38), prompt tokens synthetic  row #3x
+    cfg5                            VIMA-Gato 200M (22 layers, decoder-only), 256 episodes/GPU, L=392   configs[4] / row #5
+
+`value`     : device-timed (CUDA events), inputs resident in HBM.
+`e2e`       : wall-clock (perf_counter) over the same step through the same public methods, the new observation coming
+              from pinned HOST memory (H2D inside the timed region), the action indices read back to the host every step.
+`cpu_baseline` / `--impl reference`: the UNMODIFIED reference (oracle/_ref, staged by oracle/make_ref.py; the oracle port
+              if it is not staged) on the box's host cores, fixed thread count, a bounded sample of the same workload.
+              bench.py runs the same `--impl reference` code in a subprocess, so the two numbers share one code path.
+`gpu_eager` : the same unmodified reference in PyTorch eager on the SAME GPU (fp32, and TF32-allowed), full batch, with the
+              rel-L2 between its outputs and ours on identical inputs and weights.
 """
 from __future__ import annotations
 
@@ -25,6 +36,7 @@ import subprocess
 import sys
 import threading
 import time
+from dataclasses import replace
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -32,6 +44,9 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 METRIC = "policy steps/sec (batched action decode)"
+# Host threads of the CPU arm: fixed (no search).  torch's CPU GEMMs stop scaling well before the 100+ cores of a GPU
+# box and collapse when oversubscribed, so the arm uses min(cores, CPU_THREADS) intra-op threads and says so.
+CPU_THREADS = 32
 
 
 def parse():
@@ -40,42 +55,187 @@ def parse():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg3")
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2", "cfg3x", "cfg5"])
     ap.add_argument("--precision", default="f16f8")
     ap.add_argument("--batch", type=int, default=0, help="episodes per GPU (default: the workload's)")
-    ap.add_argument("--cpu-episodes", type=int, default=4, help="episodes in the CPU baseline sample")
+    ap.add_argument("--ragged", action="store_true", help="ragged prompts + random object masks (the masked attention branches)")
+    ap.add_argument("--graph", action="store_true", help="replay the step from a CUDA graph")
+    ap.add_argument("--cpu-episodes", type=int, default=8, help="episodes in the CPU reference sample")
+    ap.add_argument("--cpu-threads", type=int, default=0, help="override CPU_THREADS (probing only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-fast-modes", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true")
+    ap.add_argument("--no-incremental", action="store_true")
     return ap.parse_args()
 
 
 # ------------------------------------------------------------------------------------------------------------
-# workload
+# workloads
 # ------------------------------------------------------------------------------------------------------------
-def workload_case(name: str, batch: int):
-    from dataclasses import replace
+class Workload:
+    def __init__(self, name: str, batch: int = 0, ragged: bool = False):
+        from oracle import synth
 
+        self.name = name
+        self.kind = "gato" if name == "cfg5" else "vima"
+        self.xattn_n_positions = None
+        self.synthetic_prompt = False
+        if name == "cfg5":
+            case = synth.GATO_CASES["gato_cfg5"]
+            self.cfg = dict(synth.GATO_CFGS[case.model])
+            self.model_name = "VIMA-Gato 200M (22 layers, 24 heads, decoder-only)"
+        elif name == "cfg3x":
+            case = replace(synth.CASES["cfg3"], name="cfg3x", n_words=480, seed=18)  # Lp = 480 + 32 = 512
+            self.cfg = dict(synth.MODEL_CFGS[case.model])
+            self.xattn_n_positions, self.synthetic_prompt = 512, True
+            self.model_name = "VIMA-200M with XAttnGPT(xattn_n_positions=512)"
+        else:
+            case = synth.CASES[name]
+            self.cfg = dict(synth.MODEL_CFGS[case.model])
+            self.model_name = f"VIMA-{case.model}"
+        if batch:
+            case = replace(case, B=batch)
+        if ragged:
+            case = replace(case, ragged=True)
+        self.case = case
+        self.E = self.cfg["embed_dim"]
+        self.Q = 16 if self.kind == "gato" else case.Q  # Gato: 8 patch tokens per 64x128 view, two views
+        self.T, self.Lp = case.T, case.Lp if self.kind == "vima" else case.n_words + case.n_imgs * 16
+        self.Ls = self.T * self.Q + self.T - 1
+        self.L = self.Ls if self.kind == "vima" else self.Lp + 1 + self.Ls
+
+    def with_batch(self, B: int, seed_shift: int = 0) -> "Workload":
+        w = Workload.__new__(Workload)
+        w.__dict__.update(self.__dict__)
+        w.case = replace(self.case, B=B, seed=self.case.seed + seed_shift)
+        return w
+
+    # algorithmic FLOPs (2MNK per GEMM, attention dense incl. the masked half) per episode-step
+    def flops_per_episode_step(self) -> float:
+        E, L, Lp = self.E, self.L, self.Lp
+        heads = 12 * 2 * (512 * E + 512 * 512) + 2 * 512 * 700
+        if self.kind == "gato":
+            nl = self.cfg["n_layer"]
+            dec = nl * (32 * L * E * E + 4 * L * L * E)
+            # new observation: 2 views x (patch embed 8 x 3072 x 768 + 4 ViT layers x 24 S W^2) + fusion
+            obj = 2 * (2 * 8 * 3072 * 768 + 4 * 24 * 8 * 768 * 768) + 2 * 16 * (E + 2) * E
+            return dec + obj + heads
+        nl = self.cfg["xf_n_layers"]
+        dec = nl * (60 * L * E * E + 4 * Lp * E * E + 4 * L * Lp * E + 4 * L * L * E)
+        obj = self.Q * (0.286e9 + 2.4e6 + 2 * 1536 * E)
+        return dec + obj + heads
+
+    def describe(self) -> str:
+        c = self.case
+        extra = ", ragged prompts + random object masks" if c.ragged else ""
+        if self.kind == "gato":
+            return (f"{self.name}: {self.model_name} policy step (full-history re-forward, one causal sequence prompt|sep|history), "
+                    f"{c.B} episodes/GPU, Q={self.Q} image tokens/obs, Lp={self.Lp}, T={self.T} (L={self.L}){extra}")
+        return (f"{self.name}: {self.model_name} policy step (full-history re-forward), {c.B} episodes/GPU, Q={self.Q} object tokens, "
+                f"Lp={self.Lp} prompt tokens, T={self.T}-step history (L={self.L}){extra}")
+
+    def config(self, world: int) -> dict:
+        """Identical for both arms (the driver compares them)."""
+        cfg = {"workload": self.describe(), "global_batch": world * self.case.B, "parallelism": f"dp{world}",
+               "l2": "inputs larger than L2: activations and packed weights stream from HBM every step (L2 = 126 MB)"}
+        if self.name == "cfg3":
+            cfg["prompt_len_note"] = ("Lp=256 is BASELINE.md section 4 row #3 / SURVEY 8(d) #3: the reference VIMAPolicy caps prompts at "
+                                      "xattn_n_positions=256 (vima_policy.py:26-38); the 512-token prompt is workload cfg3x")
+        return cfg
+
+
+def wrap_dd(DD, x):
+    """nested dict -> nested DataDict (the reference's DataDict does not wrap inner dicts itself)."""
+    if isinstance(x, dict):
+        return DD({k: wrap_dd(DD, v) for k, v in x.items()})
+    return x
+
+
+def to_dev(x, dev, non_blocking=False):
+    if isinstance(x, dict):
+        return {k: to_dev(v, dev, non_blocking) for k, v in x.items()}
+    return x.to(dev, non_blocking=non_blocking)
+
+
+def pin(x):
+    if isinstance(x, dict):
+        return {k: pin(v) for k, v in x.items()}
+    return x.pin_memory()
+
+
+def nbytes(x):
+    if isinstance(x, dict):
+        return sum(nbytes(v) for v in x.values())
+    return x.numel() * x.element_size()
+
+
+def host_inputs(wl: Workload):
+    """Seeded CPU tensors of one rank: history observations, past actions, the new observation."""
     from oracle import synth
 
-    case = synth.CASES[name]
-    if batch:
-        case = replace(case, B=batch)
-    return case
+    c = wl.case
+    if wl.kind == "gato":
+        return dict(hist=synth.make_gato_obs(c, T=c.T - 1, tag="hist"), acts=synth.make_actions(c, c.T), new=synth.make_gato_obs(c, T=1, tag="new"))
+    return dict(hist=synth.make_obs(c, T=c.T - 1, tag="hist"), acts=synth.make_actions(c, c.T), new=synth.make_obs(c, T=1, tag="new"))
 
 
-def algorithmic_flops_per_episode_step(case):
-    """decoder + object encoder (new obs) + heads, per episode-step."""
-    from oracle import synth
+def synthetic_prompt(wl: Workload, dev):
+    from oracle import detgen
 
-    cfg = synth.MODEL_CFGS[case.model]
-    E, nl = cfg["embed_dim"], cfg["xf_n_layers"]
-    L, Lp, Q = case.L, case.Lp, case.Q
-    dec = nl * (60 * L * E * E + 4 * Lp * E * E + 4 * L * Lp * E + 4 * L * L * E)
-    obj = Q * (0.286e9 + 2.4e6 + 2 * 1536 * E)
-    heads = 12 * 2 * (512 * E + 512 * 512) + 2 * 512 * 700
-    return dec + obj + heads
+    c = wl.case
+    tok = detgen.uniform(f"bench.prompt.{wl.name}", (wl.Lp, c.B, wl.E), c.seed).to(dev)
+    msk = torch.ones(c.B, wl.Lp, dtype=torch.bool, device=dev)
+    if c.ragged:  # valid length ~U[Lp/2, Lp], episode 0 full
+        n = detgen.randint(f"bench.prompt_len.{wl.name}", (c.B,), wl.Lp // 2, wl.Lp + 1, c.seed).to(dev)
+        n[0] = wl.Lp
+        msk = torch.arange(wl.Lp, device=dev)[None, :] < n[:, None]
+    return tok, msk
 
 
+class Stepper:
+    """The policy step of scripts/example.py:125-198 over any object with the reference's public policy API (ours or the
+    reference's own class, on any device)."""
+
+    def __init__(self, policy, DD, wl: Workload, dev, inputs, prompt_tokens, prompt_masks):
+        self.policy, self.DD, self.wl, self.dev = policy, DD, wl, dev
+        self.gato = wl.kind == "gato"
+        self.prompt_tokens, self.prompt_masks = prompt_tokens, prompt_masks
+        hist = wrap_dd(DD, to_dev(inputs["hist"], dev))
+        if self.gato:
+            self.h_tok, self.h_msk = policy.forward_obs_token(hist), None
+        else:
+            self.h_tok, self.h_msk = policy.forward_obs_token(hist)
+        self.a_tok = policy.forward_action_token(to_dev(inputs["acts"], dev))
+        self.last_pred = None
+
+    def __call__(self, obs_dev):
+        p = self.policy
+        if self.gato:
+            n_tok = p.forward_obs_token(wrap_dd(self.DD, obs_dev))
+            pred = p.forward(obs_token=torch.cat([self.h_tok, n_tok], dim=0), action_token=self.a_tok, prompt_token=self.prompt_tokens,
+                             prompt_token_mask=self.prompt_masks)
+        else:
+            n_tok, n_msk = p.forward_obs_token(wrap_dd(self.DD, obs_dev))
+            pred = p.forward(obs_token=torch.cat([self.h_tok, n_tok], dim=0), obs_mask=torch.cat([self.h_msk, n_msk], dim=0),
+                             action_token=self.a_tok, prompt_token=self.prompt_tokens, prompt_token_mask=self.prompt_masks)
+        self.last_pred = pred[-1:]
+        dists = p.forward_action_decoder(pred[-1:])
+        modes = {k: v.mode() for k, v in dists.items()}
+        nxt = p.forward_action_token({k: v.clone() for k, v in modes.items()})
+        return dists, modes, nxt
+
+
+def raw_logits(dists) -> torch.Tensor:
+    """[B, 700] un-normalised head outputs in ActionDecoder key order (ours expose them; the all-gather payload)."""
+    return torch.cat([dists[k].raw_logits for k in dists], dim=-1).reshape(-1, 700).contiguous()
+
+
+def norm_logits(dists) -> torch.Tensor:
+    return torch.cat([d.logits for k in dists for d in dists[k]._dists], dim=-1).reshape(-1, 700)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------------
 def sample_clocks(stop_evt, out):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -118,105 +278,132 @@ def summarise_clocks(lines):
 
 
 # ------------------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port on host cores
+# reference arm: the unmodified reference (oracle/_ref) on host cores; the oracle port when it is not staged
 # ------------------------------------------------------------------------------------------------------------
-def cpu_oracle_steps(case_name: str, n_episodes: int, reps: int):
-    """Times `reps` policy steps of `n_episodes` episodes on the CPU oracle. Returns (steps/sec, cores, seconds list)."""
-    from dataclasses import replace
+def build_reference_policy(wl: Workload, dev):
+    """The reference's own policy class, filled with the shared deterministic weights. Returns (policy, DataDict)."""
+    from oracle import detgen
+    from oracle.ref_shim import load_reference
 
+    ref = load_reference()
+    DD = sys.modules["vima.utils"].DataDict
+    torch.manual_seed(0)
+    if wl.kind == "gato":
+        pol = ref.VIMAGatoPolicy(**wl.cfg)
+    else:
+        pol = ref.VIMAPolicy(**wl.cfg)
+        if wl.xattn_n_positions is not None:  # cfg3x: same decoder class with the longer cross-attention position table
+            import vima.nn as rnn
+
+            pol.xattn_gpt = rnn.XAttnGPT(wl.E, n_layer=wl.cfg["xf_n_layers"], n_head=wl.cfg["sattn_n_heads"], dropout=0.1,
+                                         xattn_n_head=wl.cfg["xattn_n_heads"], xattn_ff_expanding=4, xattn_n_positions=wl.xattn_n_positions,
+                                         use_geglu=True)
+    detgen.fill_module_(pol)
+    return pol.to(dev).eval(), DD
+
+
+def cpu_threads(args) -> int:
+    return max(1, min(os.cpu_count() or 1, args.cpu_threads or CPU_THREADS))
+
+
+def cpu_reference_steps(args, wl: Workload, n_episodes: int, warm: int, reps: int):
+    """-> (seconds per step list, kind). One step = n_episodes policy steps on the CPU."""
+    from oracle.ref_shim import reference_available
+
+    torch.set_num_threads(cpu_threads(args))
+    w = wl.with_batch(n_episodes)
+    dev = torch.device("cpu")
+    times = []
+    with torch.no_grad():
+        if reference_available():
+            kind = "reference"
+            pol, DD = build_reference_policy(w, dev)
+            ptok, pmsk = synthetic_prompt(w, dev)
+            inp = host_inputs(w)
+            st = Stepper(pol, DD, w, dev, inp, ptok, pmsk)
+            new = inp["new"]
+            fn = lambda: st(new)
+        else:  # the oracle restatement (VIMAPolicy workloads only)
+            kind = "port"
+            if w.kind != "vima" or w.xattn_n_positions:
+                raise RuntimeError("the staged reference (oracle/_ref) is missing and the oracle port only covers the VIMAPolicy workloads")
+            fn = _oracle_port_step(w)
+        for i in range(warm + reps):
+            t0 = time.perf_counter()
+            fn()
+            dt = time.perf_counter() - t0
+            if i >= warm:
+                times.append(dt)
+    return times, kind
+
+
+def _oracle_port_step(w: Workload):
     from oracle import detgen, synth, vima_oracle as O
     from oracle.state_dict_spec import state_dict_spec
 
-    case = replace(synth.CASES[case_name], B=n_episodes)
-    cfg = synth.MODEL_CFGS[case.model]
+    case, cfg = w.case, w.cfg
     skip = ("t5_prompt_encoder", "prompt_embedding", "prompt_obj_post_layer")  # prompt encode is outside the step
     sd = {}
     for k, shape in state_dict_spec(**cfg).items():
-        if k.startswith(skip):
-            continue
-        w = detgen.weight_for(k, shape)
-        if w is not None:
-            sd[k] = w
-    E = cfg["embed_dim"]
-    with torch.no_grad():
-        prompt_tokens = detgen.uniform("bench.prompt", (case.Lp, case.B, E))
-        prompt_masks = torch.ones(case.B, case.Lp, dtype=torch.bool)
-        hist = synth.make_obs(case, T=case.T - 1, tag="hist")
-        h_tok, h_msk = O.forward_obs_token(sd, hist)
-        a_tok = O.forward_action_token(sd, synth.make_actions(case, case.T))
-        new_obs = synth.make_obs(case, T=1, tag="new")
-
-        def one_step():
-            t0 = time.perf_counter()
-            O.policy_step(sd, obs=new_obs, history_obs_tokens=h_tok, history_obs_masks=h_msk, history_action_tokens=a_tok,
-                          prompt_tokens=prompt_tokens, prompt_masks=prompt_masks, n_head=cfg["sattn_n_heads"], xattn_n_head=cfg["xattn_n_heads"])
-            return time.perf_counter() - t0
-
-        # "all the host threads it can use": torch's CPU kernels stop scaling (and collapse when oversubscribed) well
-        # before 100+ threads, so pick the fastest thread count among powers of two up to the core count.
-        ncpu = os.cpu_count() or 1
-        cands = sorted({c for c in (8, 16, 32, 64, 128, 256) if c <= ncpu} | {min(ncpu, 8)})
-        best_t, best_n = None, cands[0]
-        for c in cands:
-            torch.set_num_threads(c)
-            one_step()
-            dt = one_step()
-            if best_t is None or dt < best_t:
-                best_t, best_n = dt, c
-            elif dt > 3 * best_t:
-                break
-        torch.set_num_threads(best_n)
-        times = [one_step() for _ in range(reps)]
-    med = statistics.median(times)
-    return n_episodes / med, torch.get_num_threads(), times
+        if not k.startswith(skip):
+            v = detgen.weight_for(k, shape)
+            if v is not None:
+                sd[k] = v
+    ptok, pmsk = synthetic_prompt(w, torch.device("cpu"))
+    hist = synth.make_obs(case, T=case.T - 1, tag="hist")
+    h_tok, h_msk = O.forward_obs_token(sd, hist)
+    a_tok = O.forward_action_token(sd, synth.make_actions(case, case.T))
+    new_obs = synth.make_obs(case, T=1, tag="new")
+    return lambda: O.policy_step(sd, obs=new_obs, history_obs_tokens=h_tok, history_obs_masks=h_msk, history_action_tokens=a_tok,
+                                 prompt_tokens=ptok, prompt_masks=pmsk, n_head=cfg["sattn_n_heads"], xattn_n_head=cfg["xattn_n_heads"])
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    case = workload_case(args.workload, args.batch)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    wl = Workload(args.workload, args.batch, args.ragged)
     n_ep = args.cpu_episodes
     t0 = time.perf_counter()
-    val, cores, times = cpu_oracle_steps(args.workload, n_ep, max(args.steps, 1) + max(args.warmup - 1, 0))
-    times = times[-max(args.steps, 1):]
+    times, kind = cpu_reference_steps(args, wl, n_ep, max(args.warmup, 1), max(args.steps, 1))
     ms = statistics.median(times) * 1e3
     val = n_ep / (ms / 1e3)
-    sample = f"{n_ep} episodes x {len(times)} timed steps of {args.workload} (L={case.L}, Lp={case.Lp}) on the CPU oracle port"
+    spread = (max(times) - min(times)) / statistics.median(times)
+    what = "the unmodified reference (oracle/_ref, vima.policy public API)" if kind == "reference" else "the oracle port (oracle/vima_oracle.py)"
+    sample = (f"{n_ep} episodes x {len(times)} timed steps (median; spread {spread:.2f}) of {args.workload} (L={wl.L}, Lp={wl.Lp}) on {what}, "
+              f"torch fp32, {torch.get_num_threads()} intra-op threads of {os.cpu_count()} logical cores, prompt tokens synthetic")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: VIMA-{case.model} policy step, {n_ep} episodes (bounded CPU sample), Q={case.Q}, Lp={case.Lp}, T={case.T}",
-                   "parallelism": "cpu"},
-        "cpu_baseline": {"value": val, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": wl.config(world),
+        "cpu_baseline": {"value": val, "unit": "steps/s", "cores": torch.get_num_threads(), "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-        "wall_s": time.perf_counter() - t0,
+        "gpu_launches": 0, "step_seconds": times, "wall_s": time.perf_counter() - t0,
     }
     print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_subprocess(args):
+    """Runs `bench.py --impl reference` (the code the driver's reference arm runs) in a fresh process: one code path, one number."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload, "--steps", "5", "--warmup", "2",
+           "--cpu-episodes", str(args.cpu_episodes)] + (["--ragged"] if args.ragged else []) + (["--batch", str(args.batch)] if args.batch else []) \
+        + (["--cpu-threads", str(args.cpu_threads)] if args.cpu_threads else [])
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)["cpu_baseline"]
+        return {"error": (r.stderr or r.stdout)[-400:]}
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)[:400]}
 
 
 # ------------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------------
-def to_dev(x, dev, non_blocking=False):
-    if isinstance(x, dict):
-        return {k: to_dev(v, dev, non_blocking) for k, v in x.items()}
-    return x.to(dev, non_blocking=non_blocking)
-
-
-def pin(x):
-    if isinstance(x, dict):
-        return {k: pin(v) for k, v in x.items()}
-    return x.pin_memory()
-
-
-def nbytes(x):
-    if isinstance(x, dict):
-        return sum(nbytes(v) for v in x.values())
-    return x.numel() * x.element_size()
-
-
 class GemmTimer:
     """Wraps Context.gemm with CUDA events on the launching stream: per-launch durations + algorithmic FLOPs."""
 
@@ -230,7 +417,8 @@ class GemmTimer:
             e0.record()
             self.orig(**kw)
             e1.record()
-            self.rec.append((e0, e1, 2.0 * kw["M"] * kw["N"] * kw["K"], (kw["M"], kw["N"], kw["K"])))
+            n_eff = kw["N"]
+            self.rec.append((e0, e1, 2.0 * kw["M"] * n_eff * kw["K"], (kw["M"], kw["N"], kw["K"])))
 
         ctx.gemm = timed
 
@@ -240,12 +428,89 @@ class GemmTimer:
         return tot_ms, tot_fl, len(self.rec)
 
 
+def build_our_policy(wl: Workload, dev):
+    import vima_b200
+    from oracle import detgen
+
+    if wl.kind == "gato":
+        pol = vima_b200.VIMAGatoPolicy(**wl.cfg)
+    else:
+        pol = vima_b200.VIMAPolicy(**wl.cfg)
+        if wl.xattn_n_positions is not None:
+            from vima_b200 import nn as vnn
+
+            pol.xattn_gpt = vnn.XAttnGPT(wl.E, n_layer=wl.cfg["xf_n_layers"], n_head=wl.cfg["sattn_n_heads"], dropout=0.1,
+                                         xattn_n_head=wl.cfg["xattn_n_heads"], xattn_ff_expanding=4, xattn_n_positions=wl.xattn_n_positions,
+                                         use_geglu=True)
+    detgen.fill_module_(pol)
+    return pol.to(dev).eval()
+
+
+def encode_prompt(policy, wl: Workload, dev):
+    """-> (prompt_tokens, prompt_masks, ms per batch | None). Once per episode: outside the step."""
+    from oracle import synth
+    from vima_b200.utils import DataDict
+
+    if wl.synthetic_prompt:
+        tok, msk = synthetic_prompt(wl, dev)
+        return tok, msk, None
+    prompt = synth.make_gato_prompt(wl.case) if wl.kind == "gato" else synth.make_prompt(wl.case)
+    pr_in = (prompt[0], prompt[1].to(dev), DataDict(to_dev(prompt[2], dev)))
+    policy.forward_prompt_assembly(pr_in)  # warm (weight packing)
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    tok, msk = policy.forward_prompt_assembly(pr_in)
+    e1.record(); torch.cuda.synchronize()
+    return tok, msk, e0.elapsed_time(e1)
+
+
+def gpu_eager_leg(wl: Workload, dev, inputs, prompt_tokens, prompt_masks, our_pred, our_logits_norm, our_modes, new_obs_dev):
+    """The unmodified reference in PyTorch eager on this GPU: fp32 and TF32-allowed, same batch, same inputs and weights."""
+    from oracle.ref_shim import reference_available
+
+    if not reference_available():
+        return {"unavailable": "oracle/_ref is not staged"}
+    out = {}
+    pol, DD = build_reference_policy(wl, dev)
+    with torch.no_grad():
+        st = Stepper(pol, DD, wl, dev, inputs, prompt_tokens.contiguous(), prompt_masks)
+        for mode, tf32 in (("fp32", False), ("tf32", True)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            for _ in range(2):
+                dists, modes, _ = st(new_obs_dev)
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(3):
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                dists, modes, _ = st(new_obs_dev)
+                e1.record(); torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            ms = statistics.median(ts)
+            ref_pred = st.last_pred.float()
+            ref_ln = norm_logits(dists).float()
+            rl2 = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+            agree = [float((modes[k] == our_modes[k]).float().mean()) for k in modes]
+            out[mode] = {"ms_per_step": ms, "value": wl.case.B / (ms / 1e3), "unit": "steps/s",
+                         "ours_vs_this_rel_l2": {"predicted_token": rl2(our_pred, ref_pred), "normalised_logits": rl2(our_logits_norm, ref_ln)},
+                         "action_index_agreement": min(agree)}
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+    out["what"] = ("unmodified reference (oracle/_ref) through its public policy API, PyTorch eager on the same GPU, same "
+                   f"{wl.case.B}-episode batch, same weights/inputs; 3 timed steps (median) after 2 warm-ups")
+    del st, pol
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     import torch.distributed as dist
 
     import vima_b200
-    from oracle import detgen, synth
     from vima_b200 import _C
+    from vima_b200.dist import all_gather_logits
     from vima_b200.utils import DataDict
 
     rank = int(os.environ.get("RANK", "0"))
@@ -256,48 +521,34 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     vima_b200.set_precision(args.precision)
-    case = workload_case(args.workload, args.batch)
-    case = type(case)(**{**case.__dict__, "seed": case.seed + rank})  # independent episodes per rank
-    cfg = synth.MODEL_CFGS[case.model]
+    wl0 = Workload(args.workload, args.batch, args.ragged)
+    wl = wl0.with_batch(wl0.case.B, seed_shift=rank)  # independent episodes per rank
+    B, T, Q = wl.case.B, wl.T, wl.Q
     t_setup = time.perf_counter()
-    policy = vima_b200.VIMAPolicy(**cfg)
-    detgen.fill_module_(policy)
-    policy = policy.to(dev).eval()
+    policy = build_our_policy(wl, dev)
     ctx = _C.Context.get(dev)
-    B, T, Q, E = case.B, case.T, case.Q, cfg["embed_dim"]
 
     with torch.no_grad():
-        # ---- once per episode: prompt encode (untimed here, reported) ----
-        prompt = synth.make_prompt(case)
-        pr_in = (prompt[0], prompt[1].to(dev), DataDict(to_dev(prompt[2], dev)))
-        policy.forward_prompt_assembly(pr_in)  # warm (weight packing)
-        torch.cuda.synchronize()
-        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record()
-        prompt_tokens, prompt_masks = policy.forward_prompt_assembly(pr_in)
-        e1.record(); torch.cuda.synchronize()
-        prompt_ms = e0.elapsed_time(e1)
-        # ---- history cache, as example.py keeps it: tokens of the T-1 earlier obs steps and actions ----
-        hist = synth.make_obs(case, T=T - 1, tag="hist")
-        h_tok, h_msk = policy.forward_obs_token(DataDict(to_dev(hist, dev)))
-        a_tok = policy.forward_action_token(to_dev(synth.make_actions(case, T), dev))
-        new_obs_host = pin(synth.make_obs(case, T=1, tag="new"))
+        prompt_tokens, prompt_masks, prompt_ms = encode_prompt(policy, wl, dev)
+        inputs = host_inputs(wl)
+        step = Stepper(policy, DataDict, wl, dev, inputs, prompt_tokens, prompt_masks)
+        new_obs_host = pin(inputs["new"])
         new_obs_dev = to_dev(new_obs_host, dev)
         gathered = torch.empty((world * B, 700), dtype=torch.float32, device=dev) if world > 1 else None
 
-        def step(obs_dev):
-            n_tok, n_msk = policy.forward_obs_token(DataDict(obs_dev))
-            obs_tok = torch.cat([h_tok, n_tok], dim=0)
-            obs_msk = torch.cat([h_msk, n_msk], dim=0)
-            pred = policy.forward(obs_token=obs_tok, obs_mask=obs_msk, action_token=a_tok, prompt_token=prompt_tokens,
-                                  prompt_token_mask=prompt_masks)
-            dists = policy.forward_action_decoder(pred[-1:])
+        def full_step(obs_dev):
+            dists, modes, nxt = step(obs_dev)
             if world > 1:  # the path's one exchange: all-gather of the action logits over NVLink
-                logits = torch.cat([dists[k].raw_logits for k in dists], dim=-1).reshape(B, 700).contiguous()
-                dist.all_gather_into_tensor(gathered, logits)
-            modes = {k: v.mode() for k, v in dists.items()}
-            nxt = policy.forward_action_token(modes)
-            return modes, nxt
+                all_gather_logits(raw_logits(dists), out=gathered)
+            return dists, modes, nxt
+
+        run_step = full_step
+        graph_note = None
+        if args.graph:
+            from vima_b200.graphs import GraphedStep
+
+            run_step = GraphedStep(full_step, new_obs_dev, warmup=max(args.warmup, 3))
+            graph_note = run_step.describe()
 
         def barrier():
             if world > 1:
@@ -306,7 +557,7 @@ def run_ours(args):
 
         gt = GemmTimer(ctx)
         for _ in range(max(args.warmup, 3)):
-            step(new_obs_dev)
+            run_step(new_obs_dev)
         barrier()
         setup_s = time.perf_counter() - t_setup
 
@@ -315,67 +566,102 @@ def run_ours(args):
         th = threading.Thread(target=sample_clocks, args=(stop, clk), daemon=True); th.start()
         time.sleep(0.3)
         launches0 = ctx.launches
-        gt.on = True
+        gt.on = not args.graph
         barrier()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         torch.cuda.nvtx.range_push("timed")
         e0.record()
         for _ in range(args.steps):
-            step(new_obs_dev)
+            run_step(new_obs_dev)
         e1.record()
         barrier()
         torch.cuda.nvtx.range_pop()
         gt.on = False
         ms_total = e0.elapsed_time(e1)
         launches = ctx.launches - launches0
+        if args.graph:
+            launches = run_step.kernels_per_replay * args.steps
         gemm_ms, gemm_fl, n_gemm = gt.summary()
 
-        # ---- timed: end to end (pinned host obs -> device, action indices -> host, every step) ----
+        # ---- timed: end to end, wall clock (pinned host obs -> device, action indices -> host, every step) ----
         h2d = nbytes(new_obs_host)
+        d2h = 0
         barrier()
         t0 = time.perf_counter()
-        e2 = torch.cuda.Event(enable_timing=True); e3 = torch.cuda.Event(enable_timing=True)
-        e2.record()
-        d2h = 0
         for _ in range(args.steps):
             obs_d = to_dev(new_obs_host, dev, non_blocking=True)
-            modes, _ = step(obs_d)
+            _, modes, _ = run_step(obs_d)
             host_modes = {k: v.cpu() for k, v in modes.items()}  # blocking read of the step's result
             d2h = sum(v.numel() * v.element_size() for v in host_modes.values())
-        e3.record()
+        torch.cuda.synchronize()
+        e2e_ms_total = (time.perf_counter() - t0) * 1e3
         barrier()
-        e2e_ms_total = max(e2.elapsed_time(e3), (time.perf_counter() - t0) * 1e3 * 0.0)
         stop.set(); th.join(timeout=3)
 
+        # ---- on hardware: the gathered logits are what each rank computed (bit for bit) ----
+        gather_check = None
+        dists, modes, _ = full_step(new_obs_dev)
+        our_pred = step.last_pred.float().clone()
+        our_ln = norm_logits(dists).float().clone()
+        our_modes = {k: v.clone() for k, v in modes.items()}
+        if world > 1:
+            mine = raw_logits(dists)
+            own_ok = bool(torch.equal(gathered[rank * B:(rank + 1) * B], mine))
+            ok_t = torch.tensor([1.0 if own_ok else 0.0], device=dev)
+            dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
+            gather_check = {"every_rank_finds_its_own_logits_in_its_slice_bit_exact": bool(ok_t.item() == 1.0)}
+            if rank == 0:  # rank 1's episodes recomputed here from the same seed must equal rank 1's gathered slice
+                wl1 = wl0.with_batch(B, seed_shift=1)
+                pt1, pm1, _ = encode_prompt(policy, wl1, dev)
+                st1 = Stepper(policy, DataDict, wl1, dev, host_inputs(wl1), pt1, pm1)
+                d1, _, _ = st1(to_dev(host_inputs(wl1)["new"], dev))
+                gather_check["rank1_slice_equals_single_gpu_recompute_bit_exact"] = bool(torch.equal(gathered[B:2 * B], raw_logits(d1)))
+                del st1
+
         # ---- separately reported: the same T-step episode decoded step by step through the K/V cache ----
-        all_tok = torch.cat([h_tok, policy.forward_obs_token(DataDict(new_obs_dev))[0]], dim=0)
-        all_msk = torch.cat([h_msk, policy.forward_obs_token(DataDict(new_obs_dev))[1]], dim=0)
         incr_ms = None
-        for rep in range(2):  # first repetition warms the allocator
-            barrier()
-            e4 = torch.cuda.Event(enable_timing=True); e5 = torch.cuda.Event(enable_timing=True)
-            e4.record()
-            cache = policy.start_decode(prompt_tokens, prompt_masks, max_tokens=T * (Q + 1) - 1)
-            for t in range(T):
-                pred_t = policy.forward_step(cache, all_tok[t:t + 1], all_msk[t:t + 1], None if t == 0 else a_tok[t - 1:t])
-                policy.forward_action_token({k: v.mode() for k, v in policy.forward_action_decoder(pred_t).items()})
-            e5.record(); barrier()
-            incr_ms = e4.elapsed_time(e5)
-            del cache
+        if wl.kind == "vima" and not args.no_incremental:
+            n_tok, n_msk = policy.forward_obs_token(DataDict(new_obs_dev))
+            all_tok = torch.cat([step.h_tok, n_tok], dim=0)
+            all_msk = torch.cat([step.h_msk, n_msk], dim=0)
+            for rep in range(2):  # first repetition warms the allocator
+                barrier()
+                e4 = torch.cuda.Event(enable_timing=True); e5 = torch.cuda.Event(enable_timing=True)
+                e4.record()
+                cache = policy.start_decode(prompt_tokens, prompt_masks, max_tokens=T * (Q + 1) - 1)
+                for t in range(T):
+                    pred_t = policy.forward_step(cache, all_tok[t:t + 1], all_msk[t:t + 1], None if t == 0 else step.a_tok[t - 1:t])
+                    policy.forward_action_token({k: v.mode() for k, v in policy.forward_action_decoder(pred_t).items()})
+                e5.record(); barrier()
+                incr_ms = e4.elapsed_time(e5)
+                del cache
 
-    def maxr(x):
+        # ---- same-GPU comparator: the unmodified reference in PyTorch eager (rank 0, N=1 only) ----
+        eager = None
+        if world == 1 and not args.no_gpu_eager:
+            try:
+                eager = gpu_eager_leg(wl, dev, inputs, prompt_tokens, prompt_masks, our_pred, our_ln, our_modes, new_obs_dev)
+            except Exception as e:  # noqa: BLE001  (a reported baseline must not take the bench line down)
+                eager = {"error": repr(e)[:500]}
+                torch.cuda.empty_cache()
+
+    def gather_floats(x):
         if world == 1:
-            return x
+            return [x]
         t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        outl = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(outl, t)
+        return [float(o.item()) for o in outl]
 
-    ms_total = maxr(ms_total)
-    e2e_ms_total = maxr(e2e_ms_total)
-    incr_ms = maxr(incr_ms)
-    ms_step = ms_total / args.steps
-    value = world * B * args.steps / (ms_total / 1e3)
-    e2e_value = world * B * args.steps / (e2e_ms_total / 1e3)
+    per_rank_ms = gather_floats(ms_total / args.steps)
+    per_rank_e2e = gather_floats(e2e_ms_total / args.steps)
+    per_rank_gemm = gather_floats(gemm_ms / args.steps)
+    ms_step = max(per_rank_ms)
+    e2e_ms_step = max(per_rank_e2e)
+    if incr_ms is not None:
+        incr_ms = max(gather_floats(incr_ms))
+    value = world * B / (ms_step / 1e3)
+    e2e_value = world * B / (e2e_ms_step / 1e3)
 
     if rank == 0:
         peaks = {}
@@ -385,43 +671,52 @@ def run_ours(args):
             pass
         peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0  # the GEMMs run inside a long step -> sustained figure
         peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "B200_PROFILING.md fallback 1.4 PF sustained (of fallback)"
-        achieved = gemm_fl / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
-        step_flops = algorithmic_flops_per_episode_step(case) * B
+        step_flops = wl.flops_per_episode_step() * B
+        roof = {"bound": "tensor", "peak": peak_tf, "unit": "TFLOP/s", "kernel": "gemm_tc_kernel (tcgen05)", "peak_source": peak_src,
+                "traffic": None, "traffic_note": "per-launch dram bytes of every kernel of the step: profiles/r2_kernel_metrics_step.txt (ncu)",
+                "step_algorithmic_tflop": step_flops / 1e12, "step_tflops": step_flops / (ms_step / 1e3) / 1e12,
+                "step_frac_of_peak": step_flops / (ms_step / 1e3) / 1e12 / peak_tf,
+                "note": ("achieved = sum(2MNK) / sum(t) over every gemm_tc_kernel launch of the timed region (CUDA events on the launching stream); "
+                         "in *x3 modes every product is 3 tensor passes, in f16f8 1 fp16 + 2 fp8 passes = 2 pass-equivalents")}
+        if gemm_ms > 0:
+            achieved = gemm_fl / (gemm_ms / 1e3) / 1e12
+            roof.update({"achieved": achieved, "frac": achieved / peak_tf, "launches_per_step": n_gemm / args.steps,
+                         "share_of_step": gemm_ms / ms_total})
+        else:  # graph replay: no per-launch events; the whole step against the peak
+            roof.update({"achieved": roof["step_tflops"], "frac": roof["step_frac_of_peak"],
+                         "note": roof["note"] + "; CUDA-graph replay: per-launch events unavailable, achieved = whole-step algorithmic rate"})
+        dtype_txt = {"f16x3": "f16 hi/lo operand pairs (3-term products, fp32-equivalent), fp32 accumulate/softmax/LN",
+                     "bf16x3": "bf16 hi/lo operand pairs (3-term), fp32 accumulate", "f16": "f16 operands, fp32 accumulate",
+                     "bf16": "bf16 operands, fp32 accumulate",
+                     "f16f8": "f16 hi*hi + e4m3 cross terms (2 tensor pass-equivalents), f16 3-term in attention, fp32 accumulate/softmax/LN"}[args.precision]
         line = {
             "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"f16x3": "f16 hi/lo operand pairs (3-term products, fp32-equivalent), fp32 accumulate/softmax/LN",
-                      "bf16x3": "bf16 hi/lo operand pairs (3-term), fp32 accumulate", "f16": "f16 operands, fp32 accumulate",
-                      "bf16": "bf16 operands, fp32 accumulate",
-                      "f16f8": "f16 hi*hi + e4m3 cross terms (decoder GEMMs; 2 tensor pass-equivalents), f16 3-term elsewhere, fp32 accumulate/softmax/LN"}[args.precision],
-            "data": "synthetic",
-            "config": {"workload": f"{args.workload}: VIMA-{case.model} policy step (full-history re-forward), {B} episodes/GPU, Q={Q} object tokens, "
-                                   f"Lp={case.Lp} prompt tokens, T={T}-step history (L={case.L})",
-                       "global_batch": world * B, "parallelism": f"dp{world}", "precision_mode": args.precision,
-                       "l2": "inputs larger than L2: >4 GB of activations + 1.6 GB of packed weights stream per step (L2 = 126 MB)",
-                       "prompt_len_note": "Lp=256 is BASELINE.md section 4 row #3 / SURVEY 8(d) #3: the reference VIMAPolicy caps prompts at "
-                                          "xattn_n_positions=256 (vima_policy.py:26-38), longer prompts raise in the reference itself",
-                       "prompt_encode_ms_per_batch": prompt_ms, "setup_s": setup_s,
-                       "steps_per_s_with_prompt_amortised": world * B * T / ((prompt_ms + T * ms_step) / 1e3)},
-            "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_total / args.steps},
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype_txt, "data": "synthetic",
+            "config": wl0.config(world),
+            "precision_mode": args.precision,
+            "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_step,
+                    "timer": "time.perf_counter around the loop (blocking .cpu() of the action indices every step)"},
             "gpu_launches": int(launches),
             "clocks": summarise_clocks(clk.get("lines")),
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                         "traffic": 1.026e9 if args.precision == "f16f8" else (1.010e9 if args.precision == "f16x3" else None),
-                         "traffic_note": "ncu dram read+write bytes of one c_fc||gated_layer launch (M=67840,N=6144,K=768), profiles/r1_summary.md sections 2/2b; algorithmic 1.05-1.06e9",
-                         "kernel": "gemm_tc_kernel (tcgen05)", "launches_per_step": n_gemm / args.steps, "share_of_step": gemm_ms / ms_total,
-                         "peak_source": peak_src,
-                         "note": ("algorithmic FLOPs 2MNK per launch; in *x3 modes every product is issued as 3 tensor-core passes "
-                                  "(f16f8: 1 fp16 pass + 2 fp8 passes), so tensor-pipe work is 3x (2x) the algorithmic figure"),
-                         "step_algorithmic_tflop": step_flops / 1e12, "step_tflops": step_flops / (ms_step / 1e3) / 1e12},
+            "roofline": roof,
+            "per_rank": {"ms_per_step": per_rank_ms, "e2e_ms_per_step": per_rank_e2e, "gemm_ms_per_step": per_rank_gemm},
+            "setup_s": setup_s,
         }
-        line["incremental"] = {"value": world * B * T / (incr_ms / 1e3), "unit": "env steps/s", "episode_ms": incr_ms,
-                               "note": f"not the graded metric: {T}-step episode decoded through the K/V cache (start_decode/forward_step, "
-                                       "decoder + heads + action embed per step; obs tokens precomputed); same predictions as the full re-forward"}
+        if prompt_ms is not None:
+            line["prompt_encode"] = {"ms_per_batch": prompt_ms,
+                                     "steps_per_s_with_prompt_amortised": world * B * T / ((prompt_ms + T * ms_step) / 1e3)}
+        if graph_note:
+            line["cuda_graph"] = graph_note
+        if gather_check is not None:
+            line["gather_check"] = gather_check
+        if incr_ms is not None:
+            line["incremental"] = {"value": world * B * T / (incr_ms / 1e3), "unit": "env steps/s", "episode_ms": incr_ms,
+                                   "note": f"not the graded metric: {T}-step episode decoded through the K/V cache (start_decode/forward_step, "
+                                           "decoder + heads + action embed per step; obs tokens precomputed); same predictions as the full re-forward"}
+        if eager is not None:
+            line["gpu_eager"] = eager
         if not args.no_cpu_baseline and world == 1:
-            v, cores, times = cpu_oracle_steps(args.workload, args.cpu_episodes, 3)
-            line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
-                                    "sample": f"{args.cpu_episodes} episodes x 3 timed steps of {args.workload} on the CPU oracle port (median)"}
+            line["cpu_baseline"] = cpu_baseline_subprocess(args)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

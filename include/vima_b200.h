@@ -18,10 +18,19 @@
  *     kernels accumulate hi*hi + lo*hi + hi*lo in fp32, which reproduces the reference's fp32 products to
  *     ~1e-5 rel end to end (DESIGN.md "operand precision").  `lo == NULL` selects single-pass mode.
  *   - `ld*` of 16-bit operand arrays must be multiples of 8 elements and base pointers 16-byte aligned (TMA).
+ *   - descriptor structs (`vima_*_desc`) start with `uint32_t struct_size` = sizeof(the struct the CALLER was compiled
+ *     against).  The library accepts any size between the struct's ABI-v4 size (the fields up to the `v4 end` comment) and its own
+ *     sizeof -- fields the caller does not know about read as zero / NULL -- and rejects everything else with
+ *     VIMA_E_INVALID, so growing a descriptor never makes an old binding read or write through garbage.
+ *     `vima_sizeof_*()` report the library's own sizes (bindings assert equality at load time).
+ *   - the calling thread's current CUDA device is saved and restored around every call.
+ *   - environment (read ONCE, in vima_create): VIMA_B200_ATTN = tc (default) | mma;  VIMA_B200_GEMM_MODE = 2cta (default) |
+ *     mcast | 1cta;  VIMA_B200_EPI_PREFETCH = 1 (default) | 0.
  */
 #ifndef VIMA_B200_H
 #define VIMA_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -29,7 +38,7 @@ extern "C" {
 #endif
 #pragma GCC visibility push(default)
 
-#define VIMA_B200_ABI_VERSION 3
+#define VIMA_B200_ABI_VERSION 4
 
 enum { VIMA_OK = 0, VIMA_E_INVALID = 1, VIMA_E_CUDA = 2, VIMA_E_UNSUPPORTED = 3 };
 enum { VIMA_DT_F16 = 0, VIMA_DT_BF16 = 1 };
@@ -43,6 +52,14 @@ int vima_create(vima_ctx** out, int device);
 void vima_destroy(vima_ctx* ctx);
 const char* vima_last_error(vima_ctx* ctx);
 int vima_sm_count(vima_ctx* ctx);
+/* Kernel-selection options, initialised from the environment in vima_create (see "environment" above) and switchable per context:
+ * key "attn" = "tc" | "mma";  "gemm_mode" = "2cta" | "mcast" | "1cta";  "epi_prefetch" = "1" | "0".  Unknown key/value: VIMA_E_INVALID. */
+int vima_set_option(vima_ctx* ctx, const char* key, const char* value);
+/* sizeof() of the descriptor structs as THIS library was compiled (bindings check their mirror structs against these). */
+int vima_sizeof_gemm_desc(void);
+int vima_sizeof_norm_desc(void);
+int vima_sizeof_attn_desc(void);
+int vima_sizeof_f32_gemm_group(void);
 /* Number of kernels this context has launched so far (bench.py's `gpu_launches`). */
 int64_t vima_launch_count(vima_ctx* ctx);
 
@@ -67,6 +84,7 @@ int vima_pack_weight_f8(vima_ctx*, const float* w, int n, int k, int transposed,
  * GLU mode: B holds, per tile of block_n accumulator columns, block_n/2 "value" rows followed by the matching
  * block_n/2 "gate" rows (see vima_glu_block_n); N = 2 * output columns. */
 typedef struct {
+  uint32_t struct_size;    /* = sizeof(vima_gemm_desc) of the caller's header */
   int M, N, K;
   const void *a_hi, *a_lo; /* [M, lda] */
   int lda;
@@ -95,7 +113,9 @@ typedef struct {
   int ldb8;
   void *out_lo8, *out_hi8;
   int ld_o8;
+  /* ---- v4 end: later releases append below; callers built against v4 pass the v4 size and the tail reads as zero ---- */
 } vima_gemm_desc;
+#define VIMA_GEMM_DESC_V4_SIZE sizeof(vima_gemm_desc)
 int vima_gemm(vima_ctx*, const vima_gemm_desc* d, void* stream);
 /* Accumulator tile width the GLU weight interleave must use for an output width of n_out columns. */
 int vima_glu_block_n(int n_out);
@@ -111,6 +131,9 @@ typedef struct {
   int n, k;
 } vima_f32_gemm_group;
 int vima_gemm_f32_grouped(vima_ctx*, const vima_f32_gemm_group* groups_dev, int n_groups, int M, int max_n, int act, void* stream);
+/* Same, with the descriptor array in HOST memory: the descriptors travel in the kernel's parameter space (16 per launch), so no
+ * device-side array has to stay alive and the call can be captured into a CUDA graph. */
+int vima_gemm_f32_grouped_host(vima_ctx*, const vima_f32_gemm_group* groups_host, int n_groups, int M, int max_n, int act, void* stream);
 
 /* ---- LayerNorm / T5 RMSNorm over rows ---------------------------------------------------------------------
  * nn.LayerNorm eps 1e-5 (components.py:19,21,128,135; vit.py:164,168,204,214) and HF T5LayerNorm
@@ -118,6 +141,7 @@ int vima_gemm_f32_grouped(vima_ctx*, const vima_f32_gemm_group* groups_dev, int 
  * and the LAST computed norm as (hi, lo) operands.  w == NULL skips norm1 (pure add / convert). cols % 4 == 0,
  * cols <= 1024. */
 typedef struct {
+  uint32_t struct_size;    /* = sizeof(vima_norm_desc) of the caller's header */
   const float* x; int64_t rows; int cols; int ldx;
   const float* add; int ld_add;
   const float* w; const float* b; float eps; int rms;
@@ -127,7 +151,9 @@ typedef struct {
   void *out_hi, *out_lo; int ld_o16;
   int dtype;
   void *out_lo8, *out_hi8; int ld_o8; /* optional e4m3 cross-term views of the last norm's output (fp16 format) */
+  /* ---- v4 end ---- */
 } vima_norm_desc;
+#define VIMA_NORM_DESC_V4_SIZE sizeof(vima_norm_desc)
 int vima_norm(vima_ctx*, const vima_norm_desc* d, void* stream);
 
 /* ---- fused masked attention -----------------------------------------------------------------------------------
@@ -136,6 +162,7 @@ int vima_norm(vima_ctx*, const vima_norm_desc* d, void* stream);
  * no scaling, shared relative-position bias + mask).  q/k/v/o pointers address head 0's first column; head h is
  * at +h*D.  key_mask: uint8 [B, Lk] (1 = attend) or NULL.  rel_bias: fp32 [H, 2*Lk-1] indexed by (j-i+Lk-1). */
 typedef struct {
+  uint32_t struct_size;    /* = sizeof(vima_attn_desc) of the caller's header */
   const void *q_hi, *q_lo; int ldq;
   const void *k_hi, *k_lo; int ldk;
   const void *v_hi, *v_lo; int ldv;
@@ -150,7 +177,9 @@ typedef struct {
   /* KV-cache addressing (incremental decode): k/v rows of batch element b start at b*kv_batch_rows (0 = Lk),
    * key_mask rows have pitch mask_ld (0 = Lk), and under `causal` query row i sits at key position q_pos0 + i. */
   int kv_batch_rows, mask_ld, q_pos0;
+  /* ---- v4 end ---- */
 } vima_attn_desc;
+#define VIMA_ATTN_DESC_V4_SIZE sizeof(vima_attn_desc)
 int vima_attention(vima_ctx*, const vima_attn_desc* d, void* stream);
 
 /* HF modeling_perceiver.py PerceiverSelfAttention (the resampler of vima/nn/obj_encoder/perceiver/perceiver.py:11-41), fp32:

@@ -1,8 +1,9 @@
-"""Import the UNMODIFIED reference (`/root/reference/vima`) in this container.
+"""Import the UNMODIFIED reference (`/root/reference/vima`, or its staged copy `oracle/_ref/vima`).
 
-TEST INFRASTRUCTURE ONLY -- used by `tests/golden/make_golden.py` to mint golden vectors and by the
-local-only cross-check in `tests/test_oracle_vs_reference.py`.  `/root/reference` does not exist on the
-GPU box, so nothing that runs there may call into this file.
+TEST / BENCH INFRASTRUCTURE ONLY -- used by `tests/golden/make_golden.py` to mint golden vectors, by the `reference`-marked
+tests, and by `bench.py`'s reference legs (`--impl reference`, `gpu_eager`).  `/root/reference` does not exist on the GPU
+box; there the bytes-identical copy staged by the committed recipe `oracle/make_ref.py` (git-ignored build artefact,
+verified against its sha256 manifest before import) is used instead.  Nothing under `vima_b200/` imports this file.
 
 The reference does not import as-is under transformers 5.x / without kornia, dm-tree and network access.
 The shims below restore the transformers-4.x symbols it imports and replace the two `from_pretrained`
@@ -23,6 +24,7 @@ import os
 import sys
 
 REFERENCE_ROOT = "/root/reference"
+STAGED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 
 T5_BASE = dict(
     vocab_size=32128,
@@ -41,8 +43,19 @@ T5_BASE = dict(
 _loaded = None
 
 
+def reference_root():
+    """/root/reference when present (build container), else the verified staged copy, else None."""
+    if os.path.isdir(os.path.join(REFERENCE_ROOT, "vima")):
+        return REFERENCE_ROOT
+    from . import make_ref
+
+    if make_ref.verify():
+        return STAGED_ROOT
+    return None
+
+
 def reference_available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "vima"))
+    return reference_root() is not None
 
 
 def load_reference():
@@ -50,14 +63,15 @@ def load_reference():
     global _loaded
     if _loaded is not None:
         return _loaded
-    if not reference_available():
-        raise RuntimeError("reference tree not present (expected on the GPU box)")
+    root = reference_root()
+    if root is None:
+        raise RuntimeError("reference tree not present and no verified staged copy under oracle/_ref (run oracle/make_ref.py in the build container)")
 
     shim_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")
     # our own drop-in alias package is also called `vima`; make sure the reference wins here
     for name in [m for m in sys.modules if m == "vima" or m.startswith("vima.")]:
         del sys.modules[name]
-    sys.path.insert(0, REFERENCE_ROOT)
+    sys.path.insert(0, root)
     sys.path.insert(0, shim_dir)
 
     import torch  # noqa: F401
@@ -127,7 +141,7 @@ def load_reference():
     if not hasattr(VIMAFlamingoPolicy, "device"):  # vima_flamingo_policy.py:141
         VIMAFlamingoPolicy.device = property(lambda s: next(s.parameters()).device)
 
-    assert ref_vima.__file__.startswith(REFERENCE_ROOT), ref_vima.__file__
+    assert ref_vima.__file__.startswith(root), ref_vima.__file__
     _loaded = ref_vima
     # leave sys.path as is: sub-imports inside the reference are lazy in places
     return ref_vima

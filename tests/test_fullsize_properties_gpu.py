@@ -15,12 +15,14 @@ from oracle import detgen, synth
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def setup():
+@pytest.fixture(scope="module", params=["f16x3", "f16f8"])
+def setup(request):
+    """Both the parity default (f16x3) and the mode bench.py runs (f16f8: e4m3 cross terms, cta_group::2 pairs, ghost tiles)."""
     import vima_b200
     from tests.policy_runner import build_policy
 
-    vima_b200.set_precision("f16x3")
+    vima_b200.set_precision(request.param)
+    request.addfinalizer(lambda: vima_b200.set_precision("f16x3"))
     case = synth.CASES["cfg3"]
     pol = build_policy(case.model)
     E = 768

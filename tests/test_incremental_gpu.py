@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("mode,tol", [("f16x3", 1e-3), ("f16f8", 1e-3)])
-@pytest.mark.parametrize("case_name", ["cfg2_small", "ragged_4M"])
+@pytest.mark.parametrize("case_name", ["cfg2_small", "ragged_4M", "cfg3_small"])  # cfg3_small: 200M shapes (11 layers, L=263, Lp=256)
 def test_cached_steps_match_full_history(case_name, mode, tol):
     import vima_b200
     from vima_b200.utils import DataDict

@@ -244,10 +244,11 @@ def ref_attention(q, k, v, scale, causal, key_mask, bias):
 
 
 @pytest.fixture(params=["mma", "tc"])
-def attn_impl(request, monkeypatch):
+def attn_impl(request, ctx):
     """Both attention kernels: mma.sync (attention.cu) and tcgen05 (attention_tc.cu; shapes it does not take fall back)."""
-    monkeypatch.setenv("VIMA_B200_ATTN", request.param)
-    return request.param
+    ctx.set_option("attn", request.param)
+    yield request.param
+    ctx.set_option("attn", "tc")
 
 
 @pytest.mark.parametrize("split", [False, True])

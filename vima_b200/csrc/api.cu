@@ -1,6 +1,7 @@
 // C ABI of libvima_b200.so (see include/vima_b200.h).  Thin: validates arguments, builds TMA tensor maps and
 // launch configurations, and forwards to the kernels.  No host synchronisation anywhere.
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
@@ -19,6 +20,26 @@ struct vima_ctx {
   char err[512];
   void* encode_tiled;  // cuTensorMapEncodeTiled
   bool gemm_attr_set;
+  // environment, read once in vima_create
+  int attn_tc;       // VIMA_B200_ATTN: tc (1, default) | mma (0)
+  int gemm_mode;     // VIMA_B200_GEMM_MODE: 1cta (0) | mcast (1) | 2cta (2, default)
+  int epi_prefetch;  // VIMA_B200_EPI_PREFETCH: L2 prefetch of the next tile's residual / multiplier rows (default 1)
+};
+
+// Restores the calling thread's CUDA device when an entry point returns (the library switches to the context's device).
+struct DeviceGuard {
+  int prev = -1;
+  bool armed = false;
+  cudaError_t enter(int dev) {
+    cudaError_t e = cudaGetDevice(&prev);
+    if (e != cudaSuccess) return e;
+    if (prev == dev) return cudaSuccess;
+    armed = true;
+    return cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    if (armed) cudaSetDevice(prev);
+  }
 };
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -39,10 +60,25 @@ static int cuda_fail(vima_ctx* c, cudaError_t e, const char* what) {
 }
 #define CHECK_CTX(c)                  \
   if (!(c)) return VIMA_E_INVALID;    \
+  DeviceGuard dev_guard_;             \
   {                                   \
-    cudaError_t e_ = cudaSetDevice((c)->device); \
+    cudaError_t e_ = dev_guard_.enter((c)->device); \
     if (e_ != cudaSuccess) return cuda_fail((c), e_, "cudaSetDevice"); \
   }
+
+// Descriptor versioning: the caller states the size of the struct it was compiled against; anything between the ABI-v4 size and
+// this library's own size is accepted (unknown tail fields read as zero), everything else is rejected before a field is touched.
+template <class D>
+static int load_desc(vima_ctx* c, const D* in, D* out, size_t min_size, const char* what) {
+  if (!in) return fail(c, VIMA_E_INVALID, "%s: null descriptor", what);
+  const uint32_t sz = in->struct_size;
+  if (sz < min_size || sz > sizeof(D))
+    return fail(c, VIMA_E_INVALID, "%s: descriptor struct_size %u outside [%zu, %zu] (C-ABI v%d): the caller was built against another vima_b200.h",
+                what, sz, min_size, sizeof(D), VIMA_B200_ABI_VERSION);
+  memset(out, 0, sizeof(D));
+  memcpy(out, in, sz);
+  return VIMA_OK;
+}
 #define LAUNCHED(c, expr, name)                          \
   {                                                      \
     cudaError_t e_ = (expr);                             \
@@ -54,6 +90,22 @@ static int cuda_fail(vima_ctx* c, cudaError_t e, const char* what) {
 extern "C" {
 
 int vima_abi_version(void) { return VIMA_B200_ABI_VERSION; }
+
+int vima_set_option(vima_ctx* c, const char* key, const char* value) {
+  if (!c) return VIMA_E_INVALID;
+  if (!key || !value) return fail(c, VIMA_E_INVALID, "set_option: null key or value");
+  if (!strcmp(key, "attn")) {
+    if (!strcmp(value, "tc")) { c->attn_tc = 1; return VIMA_OK; }
+    if (!strcmp(value, "mma")) { c->attn_tc = 0; return VIMA_OK; }
+  } else if (!strcmp(key, "gemm_mode")) {
+    if (!strcmp(value, "1cta")) { c->gemm_mode = 0; return VIMA_OK; }
+    if (!strcmp(value, "mcast")) { c->gemm_mode = 1; return VIMA_OK; }
+    if (!strcmp(value, "2cta")) { c->gemm_mode = 2; return VIMA_OK; }
+  } else if (!strcmp(key, "epi_prefetch")) {
+    if (!strcmp(value, "0") || !strcmp(value, "1")) { c->epi_prefetch = value[0] == '1'; return VIMA_OK; }
+  }
+  return fail(c, VIMA_E_INVALID, "set_option: unknown option %s=%s", key, value);
+}
 
 int vima_create(vima_ctx** out, int device) {
   if (!out) return VIMA_E_INVALID;
@@ -77,6 +129,11 @@ int vima_create(vima_ctx** out, int device) {
     return VIMA_E_CUDA;
   }
   c->encode_tiled = fn;
+  c->attn_tc = 1; c->gemm_mode = 2; c->epi_prefetch = 1;
+  if (const char* e = getenv("VIMA_B200_ATTN")) vima_set_option(c, "attn", e);  // unknown values keep the default
+  if (const char* e = getenv("VIMA_B200_GEMM_MODE")) vima_set_option(c, "gemm_mode", e);
+  if (const char* e = getenv("VIMA_B200_EPI_PREFETCH")) vima_set_option(c, "epi_prefetch", e);
+  c->err[0] = 0;
   *out = c;
   return VIMA_OK;
 }
@@ -84,6 +141,10 @@ int vima_create(vima_ctx** out, int device) {
 void vima_destroy(vima_ctx* c) { delete c; }
 const char* vima_last_error(vima_ctx* c) { return c ? c->err : "null context"; }
 int vima_sm_count(vima_ctx* c) { return c ? c->sm_count : 0; }
+int vima_sizeof_gemm_desc(void) { return (int)sizeof(vima_gemm_desc); }
+int vima_sizeof_norm_desc(void) { return (int)sizeof(vima_norm_desc); }
+int vima_sizeof_attn_desc(void) { return (int)sizeof(vima_attn_desc); }
+int vima_sizeof_f32_gemm_group(void) { return (int)sizeof(vima_f32_gemm_group); }
 int64_t vima_launch_count(vima_ctx* c) { return c ? c->launches : 0; }
 
 int vima_split_f32(vima_ctx* c, const float* x, int64_t rows, int cols, int ldx, void* hi, void* lo, int ld16, int pad_cols, float scale,
@@ -152,9 +213,12 @@ static int make_tmap(vima_ctx* c, CUtensorMap* tm, const void* base, int dtype, 
   return VIMA_OK;
 }
 
-int vima_gemm(vima_ctx* c, const vima_gemm_desc* d, void* stream) {
+int vima_gemm(vima_ctx* c, const vima_gemm_desc* d_in, void* stream) {
   CHECK_CTX(c);
-  if (!d || !d->a_hi || !d->b_hi) return fail(c, VIMA_E_INVALID, "gemm: null operand");
+  vima_gemm_desc d_local;
+  if (int rc_ = load_desc(c, d_in, &d_local, VIMA_GEMM_DESC_V4_SIZE, "gemm")) return rc_;
+  const vima_gemm_desc* d = &d_local;
+  if (!d->a_hi || !d->b_hi) return fail(c, VIMA_E_INVALID, "gemm: null operand");
   if (d->M <= 0 || d->N <= 0 || d->K <= 0) return fail(c, VIMA_E_INVALID, "gemm: empty problem");
   if ((d->lda & 7) || (d->ldb & 7) || ((uintptr_t)d->a_hi & 15) || ((uintptr_t)d->b_hi & 15))
     return fail(c, VIMA_E_INVALID, "gemm: operands need 16-byte aligned bases and ld %% 8 == 0 (lda %d ldb %d)", d->lda, d->ldb);
@@ -188,8 +252,7 @@ int vima_gemm(vima_ctx* c, const vima_gemm_desc* d, void* stream) {
   // 2-CTA clusters with a multicast B tile once there is enough work to keep every SM pair busy; VIMA_B200_NO_MCAST=1 disables
   const int tiles_m_ = (d->M + GEMM_BM - 1) / GEMM_BM, tiles_n_ = (d->N + bn - 1) / bn;
   // VIMA_B200_GEMM_MODE = 1cta | mcast | 2cta (default 2cta: cta_group::2 pairs, M = 256, each CTA stages half of the B tile)
-  static const char* mode_env = getenv("VIMA_B200_GEMM_MODE");
-  static const int mode_pref = (mode_env && !strcmp(mode_env, "1cta")) ? 0 : (mode_env && !strcmp(mode_env, "mcast")) ? 1 : 2;
+  const int mode_pref = c->gemm_mode;
   const bool pair_ok = (bn % 64) == 0 && ((tiles_m_ + 1) / 2) * tiles_n_ >= c->sm_count / 2 && tiles_m_ >= 2;
   const int mcast = (pair_ok && mode_pref == 1) ? 1 : 0;
   const int two_cta = (pair_ok && mode_pref == 2) ? 1 : 0;
@@ -212,6 +275,7 @@ int vima_gemm(vima_ctx* c, const vima_gemm_desc* d, void* stream) {
   p.split = split;
   p.dtype = d->dtype;
   p.glu = d->glu;
+  p.epi_prefetch = c->epi_prefetch;
   p.act = d->act;
   p.acc_scale = d->acc_scale == 0.f ? 1.f : d->acc_scale;
   p.bias = d->bias;
@@ -246,9 +310,21 @@ int vima_gemm_f32_grouped(vima_ctx* c, const vima_f32_gemm_group* groups_dev, in
            "simt_gemm");
 }
 
-int vima_norm(vima_ctx* c, const vima_norm_desc* d, void* stream) {
+int vima_gemm_f32_grouped_host(vima_ctx* c, const vima_f32_gemm_group* groups_host, int n_groups, int M, int max_n, int act, void* stream) {
   CHECK_CTX(c);
-  if (!d || !d->x) return fail(c, VIMA_E_INVALID, "norm: null input");
+  if (!groups_host || n_groups < 0) return fail(c, VIMA_E_INVALID, "gemm_f32_grouped_host: null groups");
+  cudaError_t e = launch_simt_gemm_grouped_host(reinterpret_cast<const SimtGemmGroup*>(groups_host), n_groups, M, max_n, act, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(c, e, "simt_gemm");
+  c->launches += (n_groups + SIMT_MAX_HOST_GROUPS - 1) / SIMT_MAX_HOST_GROUPS;
+  return VIMA_OK;
+}
+
+int vima_norm(vima_ctx* c, const vima_norm_desc* d_in, void* stream) {
+  CHECK_CTX(c);
+  vima_norm_desc d_local;
+  if (int rc_ = load_desc(c, d_in, &d_local, VIMA_NORM_DESC_V4_SIZE, "norm")) return rc_;
+  const vima_norm_desc* d = &d_local;
+  if (!d->x) return fail(c, VIMA_E_INVALID, "norm: null input");
   if ((d->cols & 3) || d->cols > 1024 || d->cols <= 0) return fail(c, VIMA_E_INVALID, "norm: cols must be a multiple of 4, <= 1024 (got %d)", d->cols);
   if ((d->ldx & 3) || (d->add && (d->ld_add & 3)) || (d->out_f32 && (d->ld_o32 & 3)) || (d->out2_f32 && (d->ld_o2 & 3)) || (d->out_hi && (d->ld_o16 & 3)))
     return fail(c, VIMA_E_INVALID, "norm: leading dimensions must be multiples of 4");
@@ -267,16 +343,18 @@ int vima_norm(vima_ctx* c, const vima_norm_desc* d, void* stream) {
   LAUNCHED(c, launch_norm(p, (cudaStream_t)stream), "norm");
 }
 
-int vima_attention(vima_ctx* c, const vima_attn_desc* d, void* stream) {
+int vima_attention(vima_ctx* c, const vima_attn_desc* d_in, void* stream) {
   CHECK_CTX(c);
-  if (!d || !d->q_hi || !d->k_hi || !d->v_hi || !d->o_hi) return fail(c, VIMA_E_INVALID, "attention: null operand");
+  vima_attn_desc d_local;
+  if (int rc_ = load_desc(c, d_in, &d_local, VIMA_ATTN_DESC_V4_SIZE, "attention")) return rc_;
+  const vima_attn_desc* d = &d_local;
+  if (!d->q_hi || !d->k_hi || !d->v_hi || !d->o_hi) return fail(c, VIMA_E_INVALID, "attention: null operand");
   if (d->D != 32 && d->D != 64) return fail(c, VIMA_E_UNSUPPORTED, "attention: head_dim %d (32 and 64 are built)", d->D);
   if ((d->ldq & 7) || (d->ldk & 7) || (d->ldv & 7) || (d->ldo & 1)) return fail(c, VIMA_E_INVALID, "attention: leading dimensions must be multiples of 8");
   const bool split = d->q_lo != nullptr;
   if (split != (d->k_lo != nullptr) || split != (d->v_lo != nullptr)) return fail(c, VIMA_E_INVALID, "attention: q/k/v lo parts must be all set or all null");
   if (d->rel_bias && d->Lq != d->Lk) return fail(c, VIMA_E_INVALID, "attention: relative bias needs Lq == Lk");
   if (!(d->scale > 0.f)) return fail(c, VIMA_E_INVALID, "attention: scale must be positive");
-  if (d->Lk > 1024) return fail(c, VIMA_E_UNSUPPORTED, "attention: Lk %d exceeds the shared-memory resident design (1024)", d->Lk);
   AttnParams p;
   p.q_hi = (const unsigned short*)d->q_hi; p.q_lo = (const unsigned short*)d->q_lo; p.ldq = d->ldq;
   p.k_hi = (const unsigned short*)d->k_hi; p.k_lo = (const unsigned short*)d->k_lo; p.ldk = d->ldk;
@@ -291,12 +369,18 @@ int vima_attention(vima_ctx* c, const vima_attn_desc* d, void* stream) {
     return fail(c, VIMA_E_INVALID, "attention: kv_batch_rows / mask_ld must cover Lk, q_pos0 >= 0");
   if ((p.o_lo8 == nullptr) != (p.o_hi8 == nullptr) || (p.o_lo8 && ((p.ldo8 & 1) || d->dtype != DT_F16)))
     return fail(c, VIMA_E_INVALID, "attention: o_lo8/o_hi8 come together (fp16 format, even ldo8)");
-  // VIMA_B200_ATTN = mma (default) | tc.  The tcgen05 kernel (head_dim 32, split operands, no bias) is 10-14 % faster on its own
-  // at the 200M decoder shapes, but inside the power-capped policy step the two are indistinguishable (A/B on one box:
-  // 84.9-85.6 vs 85.7-85.9 ms), so the simpler mma.sync kernel stays the default; both are covered by the kernel tests.
-  const char* attn_env = getenv("VIMA_B200_ATTN");
-  const bool want_tc = attn_env && !strcmp(attn_env, "tc");
-  if (want_tc && attention_tc_supported(p)) { LAUNCHED(c, launch_attention_tc(p, (cudaStream_t)stream), "attention_tc"); }
+  // tcgen05 kernel for the shapes it takes (head_dim 32, split operands, no relative bias), mma.sync kernel otherwise;
+  // VIMA_B200_ATTN=mma (read once in vima_create) forces the latter.  Both are covered by the kernel tests.
+  if (c->attn_tc && attention_tc_supported(p)) { LAUNCHED(c, launch_attention_tc(p, (cudaStream_t)stream), "attention_tc"); }
+  {
+    // the mma.sync kernel keeps K and V^T (hi + lo) of one (batch, head) resident in shared memory
+    const size_t need = attention_smem_bytes(p);
+    if (need > (size_t)c->max_smem_optin)
+      return fail(c, VIMA_E_UNSUPPORTED,
+                  "attention: Lk = %d keys of head_dim %d (%s operands%s) need %zu bytes of shared memory, the device offers %d: the "
+                  "resident-K/V kernel takes Lk <= %d at this head_dim", d->Lk, d->D, split ? "split" : "single", d->rel_bias ? ", relative bias" : "",
+                  need, c->max_smem_optin, attention_max_lk(p, (size_t)c->max_smem_optin));
+  }
   LAUNCHED(c, launch_attention(p, (cudaStream_t)stream), "attention");
 }
 

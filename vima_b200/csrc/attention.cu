@@ -303,12 +303,29 @@ __global__ void __launch_bounds__(256, (D == 32) ? 2 : 1) attention_kernel(const
   }
 }
 
-template <int D, int DT, bool SPLIT>
-static cudaError_t launch_attn_t(const AttnParams& p, cudaStream_t stream) {
+// dynamic shared memory of attention_kernel: K [Lk_pad, D+8] and V^T [D, Lk_pad+8] per operand part, mask row, tile flags, bias row
+size_t attention_smem_bytes(const AttnParams& p) {
+  const int D = p.D;
   const int Lk_pad = (p.Lk + 63) & ~63;
-  const size_t parts = SPLIT ? 2 : 1;
+  const size_t parts = p.split ? 2 : 1;
   size_t smem = parts * (size_t)Lk_pad * (D + 8) * 2 + parts * (size_t)D * (Lk_pad + 8) * 2 + (size_t)Lk_pad * 4 + (size_t)(Lk_pad / 64 + 1) * 4;
   if (p.rel_bias) smem += (size_t)(2 * p.Lk) * 4;
+  return smem;
+}
+
+int attention_max_lk(const AttnParams& p, size_t smem_limit) {
+  AttnParams q = p;
+  int best = 0;
+  for (int lk = 64; lk <= 4096; lk += 64) {
+    q.Lk = lk;
+    if (attention_smem_bytes(q) <= smem_limit) best = lk; else break;
+  }
+  return best;
+}
+
+template <int D, int DT, bool SPLIT>
+static cudaError_t launch_attn_t(const AttnParams& p, cudaStream_t stream) {
+  const size_t smem = attention_smem_bytes(p);
   auto kern = attention_kernel<D, DT, SPLIT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

@@ -9,8 +9,11 @@ namespace vima {
 constexpr int ST = 64;   // tile edge
 constexpr int SK = 16;   // k step
 
-__global__ void __launch_bounds__(256) simt_gemm_kernel(const SimtGemmGroup* __restrict__ groups, int M, int act) {
-  const SimtGemmGroup g = groups[blockIdx.z];
+struct SimtGroupsByValue {  // descriptors travel in the kernel's parameter space: no device-side array, CUDA-graph safe
+  SimtGemmGroup g[SIMT_MAX_HOST_GROUPS];
+};
+
+__device__ __forceinline__ void simt_gemm_tile(const SimtGemmGroup& g, int M, int act) {
   const int n0 = blockIdx.x * ST, m0 = blockIdx.y * ST;
   if (n0 >= g.n) return;
   __shared__ float xs[SK][ST + 4];
@@ -49,6 +52,29 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(const SimtGemmGroup* __r
       g.y[(size_t)m * g.ldy + n] = apply_act(act, v);
     }
   }
+}
+
+__global__ void __launch_bounds__(256) simt_gemm_kernel(const SimtGemmGroup* __restrict__ groups, int M, int act) {
+  const SimtGemmGroup g = groups[blockIdx.z];
+  simt_gemm_tile(g, M, act);
+}
+
+__global__ void __launch_bounds__(256) simt_gemm_kernel_v(const __grid_constant__ SimtGroupsByValue groups, int M, int act) {
+  simt_gemm_tile(groups.g[blockIdx.z], M, act);
+}
+
+cudaError_t launch_simt_gemm_grouped_host(const SimtGemmGroup* groups_host, int n_groups, int M, int max_n, int act, cudaStream_t stream) {
+  if (M == 0 || n_groups == 0) return cudaSuccess;
+  for (int g0 = 0; g0 < n_groups; g0 += SIMT_MAX_HOST_GROUPS) {
+    const int n = n_groups - g0 < SIMT_MAX_HOST_GROUPS ? n_groups - g0 : SIMT_MAX_HOST_GROUPS;
+    SimtGroupsByValue v;
+    for (int i = 0; i < SIMT_MAX_HOST_GROUPS; ++i) v.g[i] = groups_host[g0 + (i < n ? i : 0)];
+    dim3 grid((max_n + ST - 1) / ST, (M + ST - 1) / ST, n);
+    simt_gemm_kernel_v<<<grid, 256, 0, stream>>>(v, M, act);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }
 
 cudaError_t launch_simt_gemm_grouped(const SimtGemmGroup* groups_dev, int n_groups, int M, int max_n, int act, cudaStream_t stream) {

@@ -36,6 +36,7 @@ struct alignas(64) GemmParams {
   int two_cta;      // 1: launched as 2-CTA clusters running cta_group::2 MMAs (M = 256 per pair; each CTA holds half of B)
   int split;        // 0: hi*hi only, 1: three-term fp16 split product, 2: fp16 hi*hi + two fp8 cross terms
   int dtype;        // DT_F16 / DT_BF16 (operand and 16-bit output format)
+  int epi_prefetch; // 1: epilogue warps pull the next tile's residual / multiplier rows into L2 one tile ahead
   int glu;          // 1: out[:, t*bn/2 + c] = act(acc[c]+bias[c]) * (acc[bn/2+c]+bias[bn/2+c]) per tile t
   int act;
   float acc_scale;  // un-scale of pre-scaled packed weights (power of two)
@@ -411,7 +412,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     // Pull a tile's multiplier / residual rows into L2 one tile ahead of its epilogue, so the epilogue's 128-bit
     // loads are L2 hits instead of ~1 us DRAM round trips (they cannot be issued deep enough from registers).
     auto prefetch_tile = [&](int t) {
-      if (!(has_mul || has_res) || t >= num_tiles) return;
+      if (!p.epi_prefetch || !(has_mul || has_res) || t >= num_tiles) return;
       if (et >= GEMM_BM) return;
       const int row = unit_m0(t) + et;
       if (row >= p.M) return;

@@ -33,6 +33,8 @@ struct AttnParams {
   int q_pos0;                                  // causal: query row i sits at key position q_pos0 + i (incremental decode)
 };
 cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream);
+size_t attention_smem_bytes(const AttnParams& p);             // dynamic shared memory the mma.sync kernel needs for p
+int attention_max_lk(const AttnParams& p, size_t smem_limit);  // largest Lk (multiple of 64) that fits smem_limit at p's format
 bool attention_tc_supported(const AttnParams& p);  // tcgen05 variant (attention_tc.cu): head_dim 32, split operands, no bias
 cudaError_t launch_attention_tc(const AttnParams& p, cudaStream_t stream);
 
@@ -60,6 +62,8 @@ struct SimtGemmGroup {  // one fp32 problem: y[M, n] = act(x[M, k] * w[n, k]^T +
   int n, k;
 };
 cudaError_t launch_simt_gemm_grouped(const SimtGemmGroup* groups_dev, int n_groups, int M, int max_n, int act, cudaStream_t stream);
+constexpr int SIMT_MAX_HOST_GROUPS = 16;  // descriptors per launch when they travel by value (kernel parameter space)
+cudaError_t launch_simt_gemm_grouped_host(const SimtGemmGroup* groups_host, int n_groups, int M, int max_n, int act, cudaStream_t stream);
 
 // element-wise / gather kernels (misc.cu)
 cudaError_t launch_split(const float* x, long long rows, int cols, int ldx, unsigned short* hi, unsigned short* lo, int ld16,

@@ -37,11 +37,12 @@ class Conv1D(nn.Module):
 # exact-fp32 grouped GEMM helper (CUDA cores) for the tiny layers
 # ------------------------------------------------------------------------------------------------------------
 class F32GroupRunner:
-    """Caches the device-side descriptor array of one grouped fp32 GEMM launch (pointers must stay stable)."""
+    """One grouped fp32 GEMM launch.  The descriptors are built on the host and travel in the kernel's parameter space
+    (`vima_gemm_f32_grouped_host`): no device-side array, no host->device copy, capturable into a CUDA graph."""
 
     def __init__(self):
         self._key = None
-        self._dev = None
+        self._arr = None
         self._meta = None
 
     def run(self, ctx: _C.Context, groups: List[tuple], M: int, act: int):
@@ -51,11 +52,9 @@ class F32GroupRunner:
             arr = (_C.F32GemmGroup * len(groups))()
             for i, k in enumerate(key):
                 arr[i] = _C.F32GemmGroup(k[0], k[1], k[2], groups[i][2].stride(0), k[3] or None, k[4], k[5], k[6], k[7])
-            host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
-            self._dev = host.to(groups[0][0].device)
-            self._key = key
+            self._arr, self._key = arr, key
             self._meta = (len(groups), max(k[6] for k in key))
-        ctx.gemm_f32_grouped(self._dev, self._meta[0], M, self._meta[1], act)
+        ctx.gemm_f32_grouped_host(self._arr, self._meta[0], M, self._meta[1], act)
 
 
 def _use_tensor_cores(in_features: int, rows: int) -> bool:

@@ -70,8 +70,9 @@ class DecodeCache:
     causal block appends the new tokens' keys/values to `kv[i]` ([B*Lmax, 2E] (hi, lo) pairs) and attends over the
     cached prefix (`vima_attention` with kv_batch_rows / mask_ld / q_pos0)."""
 
-    def __init__(self, *, B: int, Lmax: int, E: int, n_layer: int, device, split: bool):
+    def __init__(self, *, B: int, Lmax: int, E: int, n_layer: int, device, split: bool, precision: str = ""):
         self.B, self.Lmax, self.E, self.L = B, Lmax, E, 0
+        self.precision = precision  # the operand format the K/V rows are stored in; forward_step refuses any other mode
         mk = lambda: torch.zeros((B * Lmax, 2 * E), dtype=torch.int16, device=device)
         self.kv_hi = [mk() for _ in range(n_layer)]
         self.kv_lo = [mk() if split else None for _ in range(n_layer)]
@@ -84,6 +85,16 @@ class DecodeCache:
         self.kv_hi[i].view(B, self.Lmax, 2 * E)[:, L0:L0 + Ln].copy_(qkv16.hi.view(B, Ln, -1)[:, :, E:3 * E])
         if self.kv_lo[i] is not None:
             self.kv_lo[i].view(B, self.Lmax, 2 * E)[:, L0:L0 + Ln].copy_(qkv16.lo.view(B, Ln, -1)[:, :, E:3 * E])
+
+
+def check_cache_append(cache: "DecodeCache", B: int, L: int, E: int, p) -> None:
+    """Everything that can refuse an append, BEFORE any cache state is touched (capacity, shapes, precision mode)."""
+    if cache.B != B or cache.E != E:
+        raise ValueError(f"DecodeCache(B={cache.B}, E={cache.E}) does not match the step's batch {B} / width {E}")
+    if cache.L + L > cache.Lmax:
+        raise ValueError(f"DecodeCache(B={cache.B}, Lmax={cache.Lmax}) cannot take {L} more tokens at length {cache.L}")
+    if cache.precision and cache.precision != p.name:
+        raise ValueError(f"DecodeCache was opened in precision mode {cache.precision!r}; the current mode is {p.name!r}")
 
 
 def run_block(ctx, p, W, blk: "Block", x32, x16, c16, *, B, L, E, H, omask, chain_ln=None, want16=False, out_f32=None, cache=None,
@@ -122,6 +133,58 @@ def run_block(ctx, p, W, blk: "Block", x32, x16, c16, *, B, L, E, H, omask, chai
         y32, _, nxt16 = eng.norm(ctx, s32, p, rows=M, cols=E, w=w, b=b, eps=blk.ln_2.eps, want16=want16, out_f32=out_f32, want_f32=out_f32 is None,
                                  out_f8=True)
     return y32, nxt16
+
+
+class PosIdGuard:
+    """Deferred report of out-of-range position ids (the reference's nn.Embedding raises IndexError on every call, xattn_gpt.py:
+    103-114; ids of -1 arise when an episode's first history slot is masked).  The kernels set a persistent device flag; the
+    first call of a module checks it synchronously, later calls copy it to pinned host memory asynchronously and the NEXT call
+    (or `check()`) raises -- no host synchronisation on the steady-state path."""
+
+    def __init__(self):
+        self.flag = None      # int32[1] on the device
+        self.host = None      # pinned int32[1]
+        self.event = None
+        self.checked_sync = False
+
+    def device_flag(self, dev) -> torch.Tensor:
+        if self.flag is None or self.flag.device != dev:
+            self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            self.event, self.checked_sync = None, False
+        return self.flag
+
+    def poll(self):
+        """Raise if a PREVIOUS call saw a bad id (its flag copy has landed)."""
+        if self.event is not None and self.event.query():
+            self.event = None
+            if int(self.host[0]) != 0:
+                self.reset()
+                raise IndexError("index out of range in self (a previous call passed a position id outside the embedding table)")
+
+    def after_launch(self):
+        if not self.checked_sync:
+            self.checked_sync = True
+            if int(self.flag.item()) != 0:
+                self.reset()
+                raise IndexError("index out of range in self (position id outside the embedding table)")
+            return
+        if torch.cuda.is_current_stream_capturing():
+            return
+        self.host.copy_(self.flag, non_blocking=True)
+        self.event = torch.cuda.Event()
+        self.event.record()
+
+    def check(self):
+        """Synchronous check (host sync)."""
+        if self.flag is not None and int(self.flag.item()) != 0:
+            self.reset()
+            raise IndexError("index out of range in self (position id outside the embedding table)")
+
+    def reset(self):
+        if self.flag is not None:
+            self.flag.zero_()
+        self.event = None
 
 
 class XAttention(nn.Module):
@@ -177,6 +240,11 @@ class XAttnGPT(nn.Module):
                 nn.init.normal_(m.weight, std=0.02)
         self._input_checked = False
         self._wc = eng.WeightCache()
+        self._pos_guard = PosIdGuard()
+
+    def check_errors(self):
+        """Host-synchronising check of the deferred position-id error flag (see PosIdGuard)."""
+        self._pos_guard.check()
 
     # ---------------------------------------------------------------------------------------------
     def _packed(self, ctx, p):
@@ -249,8 +317,7 @@ class XAttnGPT(nn.Module):
         if cache is not None:
             if obs_action_position_ids is None or obs_action_masks is None:
                 raise ValueError("cached decode needs absolute position ids and masks for the appended tokens")
-            if cache.L + L > cache.Lmax or cache.B != B or cache.E != E:
-                raise ValueError(f"DecodeCache(B={cache.B}, Lmax={cache.Lmax}) cannot take {L} more tokens at length {cache.L} for batch {B}")
+            check_cache_append(cache, B, L, E, p)
         if obs_action_tokens.dtype != torch.float32 or prompt_tokens.dtype != torch.float32:
             raise TypeError("XAttnGPT expects float32 tokens (xattn_gpt.py:150,152)")
         tok = obs_action_tokens if obs_action_tokens.stride(-1) == 1 else obs_action_tokens.contiguous()
@@ -272,7 +339,8 @@ class XAttnGPT(nn.Module):
 
         M, Mp, H, Hx = B * L, B * Lp, self.n_head, self.xattn_n_head
         d_s, d_x = E // H, E // Hx
-        err = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._pos_guard.poll()
+        err = self._pos_guard.device_flag(dev)
         # x = tokens + positions_embed[ids] (fp32 residual stream); kv = prompt + xattn_positions_embed[ids] (operands only)
         x32 = torch.empty((M, E), dtype=torch.float32, device=dev)
         ctx.add_pos_embed(tok, sb, sl, oa_ids, self.positions_embed.weight.detach(), B, L, E, out_f32=x32, err_flag=err)
@@ -289,9 +357,8 @@ class XAttnGPT(nn.Module):
         else:
             ctx.add_pos_embed(ptk, psb, psl, pr_ids, self.xattn_positions_embed.weight.detach(), B, Lp, E, hi=kv16.hi, lo=kv16.lo,
                               dtype=p.dtype, err_flag=err)
-        if not self._input_checked and cache is None:
-            if int(err.item()) != 0:
-                raise IndexError("index out of range in self (position id outside the embedding table)")
+        self._pos_guard.after_launch()  # first call: synchronous check; later: asynchronous copy, reported by the next call
+        if cache is None:
             self._input_checked = True
 
         layers = self._packed(ctx, p)

@@ -96,7 +96,8 @@ class VIMAPolicy(nn.Module):
         Lmax = self.xattn_gpt.n_positions if max_tokens is None else int(max_tokens)
         if not 0 < Lmax <= self.xattn_gpt.n_positions:
             raise ValueError(f"max_tokens={Lmax} outside (0, n_positions={self.xattn_gpt.n_positions}]")
-        cache = vnn.DecodeCache(B=B, Lmax=Lmax, E=E, n_layer=self.xattn_gpt.n_layer, device=prompt_token.device, split=eng.prec().split)
+        cache = vnn.DecodeCache(B=B, Lmax=Lmax, E=E, n_layer=self.xattn_gpt.n_layer, device=prompt_token.device, split=eng.prec().split,
+                                precision=eng.prec().name)
         pmask_u8 = eng.as_u8(prompt_token_mask)
         cache.prompt = (prompt_token, pmask_u8, torch.empty(pmask_u8.shape, dtype=torch.int64, device=prompt_token.device))
         ctx.mask_cumsum(pmask_u8, cache.prompt[2])
@@ -113,6 +114,10 @@ class VIMAPolicy(nn.Module):
         if (prev_action_token is None) != (cache.L == 0):
             raise ValueError("forward_step: exactly one action token per previous step is required")
         dev = obs_token.device
+        # every refusal happens before the cache is touched (a failed step must leave n_valid / L consistent)
+        from ..nn.xattn_gpt import check_cache_append
+
+        check_cache_append(cache, B, Q + (0 if prev_action_token is None else 1), E, eng.prec())
         new = obs_token[0].float().transpose(0, 1)  # (Q,B,E)
         m_new = eng.as_u8(obs_mask[0])
         if prev_action_token is not None:
@@ -122,11 +127,11 @@ class VIMAPolicy(nn.Module):
         pos = torch.empty(m_new.shape, dtype=torch.int64, device=dev)
         ctx.mask_cumsum(m_new, pos)
         pos += cache.n_valid[:, None]
-        cache.n_valid += m_new.sum(dim=1)
         prompt_token, pmask_u8, prompt_pos = cache.prompt
         out = self.xattn_gpt(obs_action_tokens=new, prompt_tokens=prompt_token, prompt_mask=pmask_u8.view(torch.bool),
                              obs_action_masks=m_new.view(torch.bool), obs_action_position_ids=pos, prompt_position_ids=prompt_pos,
                              cache=cache)
+        cache.n_valid += m_new.sum(dim=1)  # only after the decoder accepted the step
         return out[-1:]
 
     # --------------------------------------------------------------------------------------------------

@@ -47,7 +47,9 @@ def crop_objects(rgb, segm, obj_ids, *, device="cuda"):
     crops = torch.empty((N, n, 3, 32, 32), dtype=torch.uint8, device=rgb.device)
     bbox = torch.empty((N, n, 4), dtype=torch.int64, device=rgb.device)
     mask = torch.empty((N, n), dtype=torch.uint8, device=rgb.device)
-    n_valid = torch.empty((N,), dtype=torch.int32, device=rgb.device)
+    n_valid = torch.zeros((N,), dtype=torch.int32, device=rgb.device)  # zeros: an empty object list launches nothing
+    if N == 0 or n == 0:
+        return crops, bbox, mask.view(torch.bool), n_valid
     ctx.object_stats(segm, N, H, W, ids, n, per_image, stats)
     ctx.crop_resize(rgb, N, H, W, stats, n, crops, bbox, mask, n_valid)
     return crops, bbox, mask.view(torch.bool), n_valid
