@@ -25,7 +25,7 @@
  *     `vima_sizeof_*()` report the library's own sizes (bindings assert equality at load time).
  *   - the calling thread's current CUDA device is saved and restored around every call.
  *   - environment (read ONCE, in vima_create): VIMA_B200_ATTN = tc (default) | mma;  VIMA_B200_GEMM_MODE = 2cta (default) |
- *     mcast | 1cta;  VIMA_B200_EPI_PREFETCH = 1 (default) | 0.
+ *     mcast | 1cta;  VIMA_B200_EPI_PREFETCH = 0 (default) | 1.
  */
 #ifndef VIMA_B200_H
 #define VIMA_B200_H
@@ -38,7 +38,7 @@ extern "C" {
 #endif
 #pragma GCC visibility push(default)
 
-#define VIMA_B200_ABI_VERSION 4
+#define VIMA_B200_ABI_VERSION 5
 
 enum { VIMA_OK = 0, VIMA_E_INVALID = 1, VIMA_E_CUDA = 2, VIMA_E_UNSUPPORTED = 3 };
 enum { VIMA_DT_F16 = 0, VIMA_DT_BF16 = 1 };
@@ -114,11 +114,34 @@ typedef struct {
   void *out_lo8, *out_hi8;
   int ld_o8;
   /* ---- v4 end: later releases append below; callers built against v4 pass the v4 size and the tail reads as zero ---- */
+  /* v5: LayerNorm folded into the GEMM (DESIGN.md "LN folding"; components.py:128,135 `ln`, components.py:19-21 `ln_1`).
+   * A holds the UN-normalised rows x, the packed weights hold W*gamma and `bias` holds b + W*beta; the epilogue applies
+   *     v = rstd[row] * (acc*acc_scale - mean[row] * ln_c1[col]) + bias[col],   ln_c1[col] = sum_k (W*gamma)[col, k]
+   * to every accumulator column (ln_cols = 1) or only to the value half of each GLU tile (ln_cols = 2: the gate reads x).
+   * row_stats: fp32 [M, 2] = (mean, rstd) per row (vima_row_stats_finalize). */
+  const float* row_stats;
+  const float* ln_c1;    /* [N], accumulator-column order like `bias` */
+  int ln_cols;
+  /* v5: the residual rows are LayerNorm'd on the fly (post-LN block, components.py:31-36: the residual of the MLP is ln_1(s)):
+   *     r = (residual[row,col] - mean[row]) * rstd[row] * res_gamma[col] + res_beta[col],  res_stats fp32 [M, 2]. Not with GLU. */
+  const float* res_stats;
+  const float* res_gamma;
+  const float* res_beta;
+  /* v5: per-row partial (sum, sum of squares) of the stored output, one pair per (n-tile, epilogue half):
+   * stats_out fp32 [M, stats_parts, 2] with stats_parts = vima_gemm_stats_parts(N, glu, block_n). */
+  float* stats_out;
+  int stats_parts;
 } vima_gemm_desc;
-#define VIMA_GEMM_DESC_V4_SIZE sizeof(vima_gemm_desc)
+#define VIMA_GEMM_DESC_V4_SIZE offsetof(vima_gemm_desc, row_stats)
 int vima_gemm(vima_ctx*, const vima_gemm_desc* d, void* stream);
 /* Accumulator tile width the GLU weight interleave must use for an output width of n_out columns. */
 int vima_glu_block_n(int n_out);
+/* Number of partial-statistics slots per row a GEMM with N accumulator columns writes (`stats_out`); block_n 0 = the library's choice. */
+int vima_gemm_stats_parts(int N, int glu, int block_n);
+/* partial [rows, parts, 2] (sum, sum of squares over disjoint column sets covering `cols` columns) -> stats [rows, 2] =
+ * (mean, 1/sqrt(var + eps)), biased variance like nn.LayerNorm; rms != 0: (0, 1/sqrt(mean(x^2) + eps)) for a folded T5 RMSNorm
+ * (HF:modeling_t5.py:46-68). */
+int vima_row_stats_finalize(vima_ctx*, const float* partial, int64_t rows, int parts, int cols, float eps, int rms, float* stats, void* stream);
 
 /* ---- exact fp32 grouped GEMM (CUDA cores) for the tiny layers -------------------------------------------------
  * action_decoder.py:151-166 (12 MLPs E->512->512->{50|100}), action_embd.py:29-56, obj_encoder.py:86 first layer.
@@ -152,8 +175,11 @@ typedef struct {
   int dtype;
   void *out_lo8, *out_hi8; int ld_o8; /* optional e4m3 cross-term views of the last norm's output (fp16 format) */
   /* ---- v4 end ---- */
+  /* v5: (mean, rstd = 1/sqrt(var + stats_eps)) of the rows of y1 (rms != 0: (0, 1/sqrt(mean(y1^2) + stats_eps))), fp32 [rows, 2] -- the row statistics a GEMM with a folded
+   * LayerNorm (vima_gemm_desc.row_stats) takes when y1 itself, not its LayerNorm, is what gets written out. */
+  float* stats_out; float stats_eps;
 } vima_norm_desc;
-#define VIMA_NORM_DESC_V4_SIZE sizeof(vima_norm_desc)
+#define VIMA_NORM_DESC_V4_SIZE offsetof(vima_norm_desc, stats_out)
 int vima_norm(vima_ctx*, const vima_norm_desc* d, void* stream);
 
 /* ---- fused masked attention -----------------------------------------------------------------------------------

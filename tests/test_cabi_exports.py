@@ -25,7 +25,7 @@ def test_header_symbols_are_exported():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/vima_b200.h but not exported"
     assert sorted(_C.EXPORTS) == names
-    assert lib.vima_abi_version() == 4
+    assert lib.vima_abi_version() == 5
 
 
 def test_no_cpu_fallback():

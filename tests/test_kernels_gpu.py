@@ -252,7 +252,7 @@ def attn_impl(request, ctx):
 
 
 @pytest.mark.parametrize("split", [False, True])
-@pytest.mark.parametrize("case", ["self32", "cross32", "t5_64", "tiny"])
+@pytest.mark.parametrize("case", ["self32", "cross32", "t5_64", "tiny", "gato392", "cross512"])
 def test_attention(ctx, split, case, attn_impl):
     dt, tdt = DT["f16"]
     g = torch.Generator(device="cuda").manual_seed(3)
@@ -262,10 +262,14 @@ def test_attention(ctx, split, case, attn_impl):
         B, H, Lq, Lk, D, causal, scale = 2, 4, 263, 250, 32, False, 1 / math.sqrt(32)
     elif case == "t5_64":
         B, H, Lq, Lk, D, causal, scale = 2, 3, 200, 200, 64, False, 1.0
+    elif case == "gato392":  # BASELINE.json configs[4]: one causal sequence prompt | sep | history
+        B, H, Lq, Lk, D, causal, scale = 2, 3, 392, 392, 32, True, 1 / math.sqrt(32)
+    elif case == "cross512":  # survey row #3x: 512 prompt tokens
+        B, H, Lq, Lk, D, causal, scale = 2, 2, 263, 512, 32, False, 1 / math.sqrt(32)
     else:
         B, H, Lq, Lk, D, causal, scale = 1, 8, 6, 10, 32, False, 1 / math.sqrt(32)
     E = H * D
-    if case in ("self32",):
+    if case in ("self32", "gato392"):
         qkv = torch.randn(B * Lq, 3 * E, device="cuda", generator=g)
         hi, lo, ld = split_ops(ctx, qkv, dt, split)
         q = (hi, lo, ld, 0); k = (hi, lo, ld, E); v = (hi, lo, ld, 2 * E)
@@ -388,6 +392,11 @@ def test_gemm_f32_grouped(ctx):
     ctx.gemm_f32_grouped(gd, len(specs), M, 512, 1)
     for y, ref, n in refs:
         assert rel(y[:, :n], ref) < 2e-6 and (y[:, n:] == 0).all()
+        y.zero_()
+    # same launch with the descriptors travelling by value (host array; the CUDA-graph-safe form the modules use)
+    ctx.gemm_f32_grouped_host(groups, len(specs), M, 512, 1)
+    for y, ref, n in refs:
+        assert rel(y[:, :n], ref) < 2e-6 and (y[:, n:] == 0).all()
 
 
 def test_token_assembly(ctx):
@@ -491,3 +500,126 @@ def test_head_select(ctx):
     assert torch.equal(modes.cpu(), exp)
     refn = torch.cat([torch.log_softmax(x, -1) for x in torch.split(logits[0], dims, -1)], -1)
     assert rel(norm.cpu(), refn) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# LayerNorm folded into the GEMMs (DESIGN.md "LN folding"): row statistics out of one epilogue, applied in the next
+# ------------------------------------------------------------------------------------------------------------------
+def _ln(x, w, b, eps=1e-5):
+    return torch.nn.functional.layer_norm(x.double(), (x.shape[-1],), w.double(), b.double(), eps)
+
+
+@pytest.mark.parametrize("mode", ["f16x3", "f16f8", "bf16x3"])
+@pytest.mark.parametrize("M,E", [(263 * 9, 768), (130, 256), (1000, 384), (40000, 768)])
+def test_gemm_row_stats_and_folded_layernorm(ctx, mode, M, E):
+    """s = A Wo^T + res with row statistics from the epilogue  ->  GEGLU over the un-normalised s with LN folded into the weights
+    (both halves: the GPT block; value half only: XAttention)  ->  projection whose residual is LN(s) rebuilt in the epilogue.
+    Checked against fp64 torch statements of the reference modules (components.py:23-37,97-102,218-226)."""
+    import vima_b200
+    from vima_b200 import engine as eng
+
+    vima_b200.set_precision(mode)
+    try:
+        p = eng.prec()
+        g = torch.Generator(device="cuda").manual_seed(M + E)
+        rn = lambda *s: torch.randn(*s, device="cuda", generator=g)
+        A = rn(M, E)
+        Wo = rn(E, E) / math.sqrt(E)
+        res = rn(M, E) * 2.0 + 0.7  # non-zero row means
+        gam, bet = 1.0 + 0.1 * rn(E), 0.1 * rn(E)
+        W1, Wg = rn(4 * E, E) / math.sqrt(E), rn(4 * E, E) / math.sqrt(E)
+        b1 = 0.1 * rn(4 * E)
+        W2 = rn(E, 4 * E) / math.sqrt(4 * E)
+        b2 = 0.1 * rn(E)
+        a16 = eng.to_operand(ctx, A, p)
+        if p.f8:
+            a16 = eng.Opnd(M, E, "cuda", True, f8=True)
+            ctx.split(A, a16.hi, None, dtype=p.dtype)
+            ctx.split_f8(A, a16.lo8, a16.hi8)
+        pwo = eng.pack_linear(ctx, Wo, None, transposed=False, p=p, f8=True)
+        part = eng.stats_buffer(ctx, M, pwo, "cuda")
+        s32, s16 = eng.gemm(ctx, a16, pwo, p, residual=res, want_f32=True, want16=True, out_f8=True, stats_out=part)
+        st = eng.row_stats_of(ctx, part, M, E, 1e-5)
+        s_ref = A.double() @ Wo.double().t() + res.double()
+        assert rel(s32, s_ref) < 3e-5
+        mean_ref = s_ref.mean(dim=1)
+        rstd_ref = 1.0 / torch.sqrt(s_ref.var(dim=1, unbiased=False) + 1e-5)
+        assert (st[:, 0].double() - mean_ref).abs().max().item() < 2e-5 * (1 + mean_ref.abs().max().item())
+        assert ((st[:, 1].double() - rstd_ref) / rstd_ref).abs().max().item() < 2e-5
+        n_ref = _ln(s_ref, gam, bet)
+        for ln_gate in (True, False):
+            pw = eng.pack_glu(ctx, W1, b1, Wg, val_transposed=False, gate_transposed=False, p=p, f8=True, ln=(gam, bet), ln_gate=ln_gate)
+            _, h16 = eng.gemm(ctx, s16, pw, p, act=3, want16=True, out_f8=True, row_stats=st)
+            gate_in = n_ref if ln_gate else s_ref
+            h_ref = torch.nn.functional.gelu(n_ref @ W1.double().t() + b1.double()) * (gate_in @ Wg.double().t())
+            h = h16.hi.view(torch.float16 if p.dtype == 0 else torch.bfloat16)[:, : 4 * E].double()
+            if h16.lo is not None:
+                h = h + h16.lo.view(torch.float16 if p.dtype == 0 else torch.bfloat16)[:, : 4 * E].double()
+            else:
+                h = h + h16.lo8[:, : 4 * E].view(torch.float8_e4m3fn).double() / 1024.0
+            tol = 2e-4 if mode == "bf16x3" else 6e-5
+            assert rel(h, h_ref) < tol, (ln_gate, rel(h, h_ref))
+            if ln_gate:  # the block's projection: residual = LN(s), rebuilt from s32 + (mean, rstd) in the epilogue
+                pw2 = eng.pack_linear(ctx, W2, b2, transposed=False, p=p, f8=True)
+                t32, _ = eng.gemm(ctx, h16, pw2, p, residual=s32, res_ln=(st, gam, bet), want_f32=True)
+                t_ref = h_ref @ W2.double().t() + b2.double() + n_ref
+                assert rel(t32, t_ref) < tol, rel(t32, t_ref)
+        # a plain (non-GLU) Linear with a folded LayerNorm in front of it
+        pwl = eng.pack_linear(ctx, Wo, b2, transposed=False, p=p, f8=True, ln=(gam, bet))
+        y32, _ = eng.gemm(ctx, s16, pwl, p, want_f32=True, row_stats=st)
+        assert rel(y32, n_ref @ Wo.double().t() + b2.double()) < (2e-4 if mode == "bf16x3" else 6e-5)
+    finally:
+        vima_b200.set_precision("f16x3")
+
+
+def test_row_statistics_are_batch_slice_deterministic(ctx):
+    """The partial sums are reduced in a fixed order: the first rows of a big GEMM get the same statistics, bit for bit, as the
+    same rows run alone (different tile counts / cluster pairing)."""
+    import vima_b200
+    from vima_b200 import engine as eng
+
+    vima_b200.set_precision("f16f8")
+    try:
+        p = eng.prec()
+        g = torch.Generator(device="cuda").manual_seed(5)
+        M, E, n = 50000, 768, 263 * 3
+        A = torch.randn(M, E, device="cuda", generator=g)
+        Wo = torch.randn(E, E, device="cuda", generator=g) / math.sqrt(E)
+        res = torch.randn(M, E, device="cuda", generator=g)
+        pwo = eng.pack_linear(ctx, Wo, None, transposed=False, p=p, f8=True)
+        outs = []
+        for rows in (M, n):
+            a16 = eng.Opnd(rows, E, "cuda", True, f8=True)
+            ctx.split(A[:rows].contiguous(), a16.hi, None, dtype=p.dtype)
+            ctx.split_f8(A[:rows].contiguous(), a16.lo8, a16.hi8)
+            part = eng.stats_buffer(ctx, rows, pwo, "cuda")
+            eng.gemm(ctx, a16, pwo, p, residual=res[:rows].contiguous(), want_f32=True, stats_out=part)
+            outs.append(eng.row_stats_of(ctx, part, rows, E, 1e-5)[:n].clone())
+        assert torch.equal(outs[0], outs[1])
+    finally:
+        vima_b200.set_precision("f16x3")
+
+
+def test_gemm_desc_v4_size_is_still_accepted(ctx):
+    """Descriptor growth: a caller compiled against the ABI-v4 struct (no folded-LN fields) passes the v4 size and is served."""
+    import ctypes as C
+
+    from vima_b200 import _C
+
+    M, N, K = 256, 256, 64
+    A = torch.randn(M, K, device="cuda")
+    W = torch.randn(N, K, device="cuda") / 8
+    a_hi, _, lda = split_ops(ctx, A, 0, False)
+    b_hi, _, ldb = split_ops(ctx, W, 0, False)
+    out = torch.empty(M, N, device="cuda")
+    d = _C.GemmDesc()
+    d.struct_size = _C.GemmDesc.row_stats.offset  # = VIMA_GEMM_DESC_V4_SIZE
+    d.M, d.N, d.K = M, N, K
+    d.a_hi, d.lda, d.b_hi, d.ldb = a_hi.data_ptr(), lda, b_hi.data_ptr(), ldb
+    d.dtype, d.acc_scale = 0, 1.0
+    d.out_f32, d.ld_o32 = out.data_ptr(), N
+    d.row_stats = 0xDEAD0  # beyond struct_size: must never be read
+    assert ctx.lib.vima_gemm(ctx.h, C.byref(d), C.c_void_p(ctx._s())) == 0, ctx.lib.vima_last_error(ctx.h)
+    torch.cuda.synchronize()
+    ref = merge(a_hi, None, torch.float16, K).double() @ merge(b_hi, None, torch.float16, K).double().t()
+    assert rel(out, ref) < 5e-6

@@ -12,6 +12,10 @@ shapes = [  # (name, N_acc, K, glu, epilogue)
     ("gate N3072 K768 ->f32", 3072, 768, 0, "o32"),
     ("fc_glu N6144 K768 ->16", 6144, 768, 1, "o16"),
     ("mlp_proj N768 K3072 +res f32", 768, 3072, 0, "res32"),
+    # round 2: LayerNorm folded into the GEMMs
+    ("wo/c_proj N768 K768 +res f32+16 +rowstats", 768, 768, 0, "res32_16_stats"),
+    ("w1||gate N6144 K768 GEGLU, LN folded ->16", 6144, 768, 1, "o16_lna"),
+    ("mlp_proj N768 K3072 +LN(res) f32", 768, 3072, 0, "res32_lnr"),
 ]
 only = os.environ.get("GB_ONLY")
 reps = int(os.environ.get("GB_REPS", 3))
@@ -26,10 +30,15 @@ for split in (0, 1, 2):
             f8 = dict(a_lo8=mk8(M), a_hi8=mk8(M), b_hi8=mk8(N), b_lo8=mk8(N))
         n_out = N // 2 if glu else N
         kw = dict(M=M, N=N, K=K, a_hi=a_hi, a_lo=a_lo, lda=K, b_hi=b_hi, b_lo=b_lo, ldb=K, dtype=0, glu=glu, act=3 if (glu or epi == "mul16") else 0, **f8)
-        if epi in ("res32_16", "res32"): kw["residual"] = torch.zeros(M, n_out, device="cuda")
-        if epi in ("res32_16", "res32", "o32"): kw["out_f32"] = torch.empty(M, n_out, device="cuda")
+        if epi in ("res32_16", "res32", "res32_16_stats", "res32_lnr"): kw["residual"] = torch.zeros(M, n_out, device="cuda")
+        if epi in ("res32_16", "res32", "o32", "res32_16_stats", "res32_lnr"): kw["out_f32"] = torch.empty(M, n_out, device="cuda")
         if epi == "mul16": kw["mul"] = torch.ones(M, n_out, device="cuda")
-        if epi in ("res32_16", "o16", "mul16"):
+        if epi == "res32_16_stats": kw["stats_out"] = torch.empty(M, ctx.gemm_stats_parts(N, glu), 2, device="cuda")
+        if epi == "o16_lna":
+            kw["row_stats"] = torch.ones(M, 2, device="cuda"); kw["ln_c1"] = torch.zeros(N, device="cuda"); kw["ln_cols"] = 2
+        if epi == "res32_lnr":
+            kw["res_stats"] = torch.ones(M, 2, device="cuda"); kw["res_gamma"] = torch.ones(n_out, device="cuda"); kw["res_beta"] = torch.zeros(n_out, device="cuda")
+        if epi in ("res32_16", "o16", "mul16", "res32_16_stats", "o16_lna"):
             kw["out_hi"] = torch.empty(M, n_out, dtype=torch.int16, device="cuda"); kw["out_lo"] = torch.empty_like(kw["out_hi"]) if split == 1 else None
             if split == 2:
                 kw["out_lo8"] = torch.empty(M, n_out, dtype=torch.uint8, device="cuda"); kw["out_hi8"] = torch.empty_like(kw["out_lo8"])

@@ -36,6 +36,10 @@ class GemmDesc(C.Structure):
         ("a_lo8", c_void_p), ("a_hi8", c_void_p), ("lda8", c_int),
         ("b_hi8", c_void_p), ("b_lo8", c_void_p), ("ldb8", c_int),
         ("out_lo8", c_void_p), ("out_hi8", c_void_p), ("ld_o8", c_int),
+        # v5
+        ("row_stats", c_void_p), ("ln_c1", c_void_p), ("ln_cols", c_int),
+        ("res_stats", c_void_p), ("res_gamma", c_void_p), ("res_beta", c_void_p),
+        ("stats_out", c_void_p), ("stats_parts", c_int),
     ]
 
 
@@ -61,6 +65,8 @@ class NormDesc(C.Structure):
         ("out_hi", c_void_p), ("out_lo", c_void_p), ("ld_o16", c_int),
         ("dtype", c_int),
         ("out_lo8", c_void_p), ("out_hi8", c_void_p), ("ld_o8", c_int),
+        # v5
+        ("stats_out", c_void_p), ("stats_eps", c_float),
     ]
 
 
@@ -83,14 +89,14 @@ _lib: Optional[C.CDLL] = None
 
 EXPORTS = [
     "vima_abi_version", "vima_sizeof_gemm_desc", "vima_sizeof_norm_desc", "vima_sizeof_attn_desc", "vima_sizeof_f32_gemm_group", "vima_create", "vima_set_option", "vima_destroy", "vima_last_error", "vima_sm_count", "vima_launch_count",
-    "vima_split_f32", "vima_pack_weight", "vima_gemm", "vima_glu_block_n", "vima_gemm_f32_grouped", "vima_gemm_f32_grouped_host", "vima_norm",
+    "vima_split_f32", "vima_pack_weight", "vima_gemm", "vima_glu_block_n", "vima_gemm_stats_parts", "vima_row_stats_finalize", "vima_gemm_f32_grouped", "vima_gemm_f32_grouped_host", "vima_norm",
     "vima_attention", "vima_small_attention", "vima_assemble_history", "vima_mask_cumsum", "vima_add_pos_embed",
     "vima_gather_prompt", "vima_patchify", "vima_vit_tokens", "vima_bbox_norm", "vima_fill_ee", "vima_max_u8",
     "vima_action_scale", "vima_action_postprocess", "vima_latent_attention", "vima_object_stats", "vima_crop_resize", "vima_head_select", "vima_gato_positions", "vima_pack_weight_f8", "vima_split_f8",
 ]
 
 
-ABI_VERSION = 4  # include/vima_b200.h VIMA_B200_ABI_VERSION
+ABI_VERSION = 5  # include/vima_b200.h VIMA_B200_ABI_VERSION
 
 
 def load_library() -> C.CDLL:
@@ -199,13 +205,23 @@ class Context:
         self._ck(self.lib.vima_split_f8(self.h, c_void_p(x.data_ptr()), c_i64(x.shape[0]), x.shape[1], x.stride(0), c_void_p(lo8.data_ptr()),
                                         c_void_p(hi8.data_ptr()), lo8.stride(0), c_void_p(self._s())), "split_f8")
 
+    def gemm_stats_parts(self, N: int, glu: int, block_n: int = 0) -> int:
+        return int(self.lib.vima_gemm_stats_parts(int(N), int(glu), int(block_n)))
+
+    def row_stats_finalize(self, partial: torch.Tensor, cols: int, eps: float, stats: torch.Tensor, rms: bool = False):
+        """partial fp32 [rows, parts, 2] -> stats fp32 [rows, 2] = (mean, rstd)  (rms: (0, 1/sqrt(mean(x^2) + eps)))."""
+        rows, parts, _ = partial.shape
+        self._ck(self.lib.vima_row_stats_finalize(self.h, c_void_p(partial.data_ptr()), c_i64(rows), int(parts), int(cols), c_float(eps),
+                                                  int(rms), c_void_p(stats.data_ptr()), c_void_p(self._s())), "row_stats_finalize")
+
     def glu_block_n(self, n_out: int) -> int:
         return int(self.lib.vima_glu_block_n(int(n_out)))
 
     # ---------------------------------------------------------------- GEMMs
     def gemm(self, *, M, N, K, a_hi, a_lo, lda, b_hi, b_lo, ldb, dtype=DT_F16, glu=0, act=ACT_NONE, acc_scale=1.0, bias=None,
              mul=None, residual=None, out_f32=None, out_hi=None, out_lo=None, ld_o16=0, block_n=0, a_lo8=None, a_hi8=None, b_hi8=None,
-             b_lo8=None, out_lo8=None, out_hi8=None):
+             b_lo8=None, out_lo8=None, out_hi8=None, row_stats=None, ln_c1=None, ln_cols=0, res_stats=None, res_gamma=None, res_beta=None,
+             stats_out=None):
         d = GemmDesc()
         d.struct_size = C.sizeof(GemmDesc)
         d.M, d.N, d.K = int(M), int(N), int(K)
@@ -221,6 +237,9 @@ class Context:
         d.a_lo8, d.a_hi8, d.lda8 = _ptr(a_lo8), _ptr(a_hi8), (a_lo8.stride(0) if a_lo8 is not None else 0)
         d.b_hi8, d.b_lo8, d.ldb8 = _ptr(b_hi8), _ptr(b_lo8), (b_hi8.stride(0) if b_hi8 is not None else 0)
         d.out_lo8, d.out_hi8, d.ld_o8 = _ptr(out_lo8), _ptr(out_hi8), (out_lo8.stride(0) if out_lo8 is not None else 0)
+        d.row_stats, d.ln_c1, d.ln_cols = _ptr(row_stats), _ptr(ln_c1), int(ln_cols)
+        d.res_stats, d.res_gamma, d.res_beta = _ptr(res_stats), _ptr(res_gamma), _ptr(res_beta)
+        d.stats_out, d.stats_parts = _ptr(stats_out), (stats_out.shape[1] if stats_out is not None else 0)
         self._ck(self.lib.vima_gemm(self.h, C.byref(d), c_void_p(self._s())), "gemm")
 
     def gemm_f32_grouped(self, groups_dev: torch.Tensor, n_groups: int, M: int, max_n: int, act: int):
@@ -233,7 +252,7 @@ class Context:
 
     # ---------------------------------------------------------------- norm / attention
     def norm(self, x, *, rows, cols, ldx, w=None, b=None, eps=1e-5, rms=0, add=None, w2=None, b2=None, eps2=1e-5, out_f32=None,
-             out2_f32=None, out_hi=None, out_lo=None, dtype=DT_F16, out_lo8=None, out_hi8=None):
+             out2_f32=None, out_hi=None, out_lo=None, dtype=DT_F16, out_lo8=None, out_hi8=None, stats_out=None, stats_eps=1e-5):
         d = NormDesc()
         d.struct_size = C.sizeof(NormDesc)
         d.x, d.rows, d.cols, d.ldx = x.data_ptr(), int(rows), int(cols), int(ldx)
@@ -245,6 +264,7 @@ class Context:
         d.out_hi, d.out_lo, d.ld_o16 = _ptr(out_hi), _ptr(out_lo), (out_hi.stride(0) if out_hi is not None else 0)
         d.dtype = dtype
         d.out_lo8, d.out_hi8, d.ld_o8 = _ptr(out_lo8), _ptr(out_hi8), (out_lo8.stride(0) if out_lo8 is not None else 0)
+        d.stats_out, d.stats_eps = _ptr(stats_out), float(stats_eps)
         self._ck(self.lib.vima_norm(self.h, C.byref(d), c_void_p(self._s())), "norm")
 
     def attention(self, *, q, k, v, o, B, H, Lq, Lk, D, scale, causal=False, key_mask=None, rel_bias=None, dtype=DT_F16, o8=None,

@@ -23,7 +23,7 @@ struct vima_ctx {
   // environment, read once in vima_create
   int attn_tc;       // VIMA_B200_ATTN: tc (1, default) | mma (0)
   int gemm_mode;     // VIMA_B200_GEMM_MODE: 1cta (0) | mcast (1) | 2cta (2, default)
-  int epi_prefetch;  // VIMA_B200_EPI_PREFETCH: L2 prefetch of the next tile's residual / multiplier rows (default 1)
+  int epi_prefetch;  // VIMA_B200_EPI_PREFETCH: L2 prefetch of the next tile's residual / multiplier rows (default 0: A/B in profiles/r2_summary.md)
 };
 
 // Restores the calling thread's CUDA device when an entry point returns (the library switches to the context's device).
@@ -129,7 +129,7 @@ int vima_create(vima_ctx** out, int device) {
     return VIMA_E_CUDA;
   }
   c->encode_tiled = fn;
-  c->attn_tc = 1; c->gemm_mode = 2; c->epi_prefetch = 1;
+  c->attn_tc = 1; c->gemm_mode = 2; c->epi_prefetch = 0;
   if (const char* e = getenv("VIMA_B200_ATTN")) vima_set_option(c, "attn", e);  // unknown values keep the default
   if (const char* e = getenv("VIMA_B200_GEMM_MODE")) vima_set_option(c, "gemm_mode", e);
   if (const char* e = getenv("VIMA_B200_EPI_PREFETCH")) vima_set_option(c, "epi_prefetch", e);
@@ -186,6 +186,17 @@ static int choose_block_n(int N, int glu) {
   return best;
 }
 int vima_glu_block_n(int n_out) { return choose_block_n(2 * n_out, 1); }
+int vima_gemm_stats_parts(int N, int glu, int block_n) {
+  const int bn = block_n > 0 ? block_n : choose_block_n(N, glu);
+  return 2 * ((N + bn - 1) / bn);
+}
+
+int vima_row_stats_finalize(vima_ctx* c, const float* partial, int64_t rows, int parts, int cols, float eps, int rms, float* stats, void* stream) {
+  CHECK_CTX(c);
+  if (!partial || !stats || rows < 0 || parts <= 0 || cols <= 0 || ((uintptr_t)partial & 7) || ((uintptr_t)stats & 7))
+    return fail(c, VIMA_E_INVALID, "row_stats_finalize: bad arguments");
+  LAUNCHED(c, launch_row_stats_finalize(partial, rows, parts, cols, eps, rms, stats, (cudaStream_t)stream), "row_stats_finalize");
+}
 
 // fp8 operand tile: rows of 64 bytes (64 K-elements), 64-byte swizzle
 static int make_tmap_f8(vima_ctx* c, CUtensorMap* tm, const void* base, int rows, int cols, int ld, int box_rows) {
@@ -245,6 +256,19 @@ int vima_gemm(vima_ctx* c, const vima_gemm_desc* d_in, void* stream) {
     if (bad) return fail(c, VIMA_E_INVALID, "gemm: epilogue tensors need N %% 4 == 0, ld %% 4 == 0 and 16-byte (fp32) / 8-byte (16-bit) aligned bases");
   }
 
+  if (d->row_stats) {
+    if (!d->ln_c1 || (d->ln_cols != 1 && d->ln_cols != 2) || (d->ln_cols == 2 && !d->glu) || ((uintptr_t)d->row_stats & 7))
+      return fail(c, VIMA_E_INVALID, "gemm: folded LayerNorm needs row_stats (8-byte aligned), ln_c1 and ln_cols 1 (all columns) or 2 (GLU value half)");
+  }
+  if (d->res_stats) {
+    if (!d->residual || !d->res_gamma || !d->res_beta || d->glu || ((uintptr_t)d->res_stats & 7))
+      return fail(c, VIMA_E_INVALID, "gemm: a LayerNorm'd residual needs residual, res_stats (8-byte aligned), res_gamma, res_beta and no GLU");
+  }
+  if (d->stats_out) {
+    if (d->stats_parts != 2 * ((d->N + bn - 1) / bn) || ((uintptr_t)d->stats_out & 7))
+      return fail(c, VIMA_E_INVALID, "gemm: stats_parts must be vima_gemm_stats_parts(N, glu, block_n) = %d (got %d)", 2 * ((d->N + bn - 1) / bn), d->stats_parts);
+  }
+
   GemmParams p;
   memset(&p, 0, sizeof(p));
   const int split = f8 ? 2 : (d->a_lo != nullptr ? 1 : 0);
@@ -284,6 +308,9 @@ int vima_gemm(vima_ctx* c, const vima_gemm_desc* d_in, void* stream) {
   p.out_f32 = d->out_f32; p.ld_o32 = d->ld_o32;
   p.out_hi = (unsigned short*)d->out_hi; p.out_lo = (unsigned short*)d->out_lo; p.ld_o16 = d->ld_o16;
   p.out_lo8 = (unsigned char*)d->out_lo8; p.out_hi8 = (unsigned char*)d->out_hi8; p.ld_o8 = d->ld_o8;
+  p.row_stats = d->row_stats; p.ln_c1 = d->ln_c1; p.ln_cols = d->ln_cols;
+  p.res_stats = d->res_stats; p.res_gamma = d->res_gamma; p.res_beta = d->res_beta;
+  p.stats_out = d->stats_out; p.stats_parts = d->stats_parts;
 
   const size_t stage = (size_t)(GEMM_A_TILE_BYTES + (two_cta ? bn / 2 : bn) * 128) * (split ? 2 : 1);
   const size_t fixed = gemm_smem_bytes(bn, split, 0, two_cta);
@@ -298,6 +325,7 @@ int vima_gemm(vima_ctx* c, const vima_gemm_desc* d_in, void* stream) {
   GemmLaunch l;
   l.act = d->act; l.glu = d->glu != 0; l.mul = d->mul != nullptr; l.res = d->residual != nullptr;
   l.o32 = d->out_f32 != nullptr; l.o16 = d->out_hi != nullptr; l.dtype = d->dtype;
+  l.lna = d->row_stats != nullptr; l.lnr = d->res_stats != nullptr; l.stats = d->stats_out != nullptr; l.device = c->device;
   if (d->dtype == DT_BF16) { LAUNCHED(c, launch_gemm_tc_bf16(p, l, grid, smem, c->max_smem_optin, (cudaStream_t)stream), "gemm_tc_kernel"); }
   LAUNCHED(c, launch_gemm_tc_f16(p, l, grid, smem, c->max_smem_optin, (cudaStream_t)stream), "gemm_tc_kernel");
 }
@@ -338,6 +366,8 @@ int vima_norm(vima_ctx* c, const vima_norm_desc* d_in, void* stream) {
   p.out_hi = (unsigned short*)d->out_hi; p.out_lo = (unsigned short*)d->out_lo; p.ld_o16 = d->ld_o16;
   p.dtype = d->dtype;
   p.out_lo8 = (unsigned char*)d->out_lo8; p.out_hi8 = (unsigned char*)d->out_hi8; p.ld_o8 = d->ld_o8;
+  p.stats_out = d->stats_out; p.stats_eps = d->stats_eps;
+  if (p.stats_out && ((uintptr_t)p.stats_out & 7)) return fail(c, VIMA_E_INVALID, "norm: stats_out must be 8-byte aligned");
   if ((p.out_lo8 == nullptr) != (p.out_hi8 == nullptr) || (p.out_lo8 && (p.ld_o8 & 3)))
     return fail(c, VIMA_E_INVALID, "norm: out_lo8/out_hi8 come together with ld_o8 %% 4 == 0");
   LAUNCHED(c, launch_norm(p, (cudaStream_t)stream), "norm");
@@ -371,7 +401,7 @@ int vima_attention(vima_ctx* c, const vima_attn_desc* d_in, void* stream) {
     return fail(c, VIMA_E_INVALID, "attention: o_lo8/o_hi8 come together (fp16 format, even ldo8)");
   // tcgen05 kernel for the shapes it takes (head_dim 32, split operands, no relative bias), mma.sync kernel otherwise;
   // VIMA_B200_ATTN=mma (read once in vima_create) forces the latter.  Both are covered by the kernel tests.
-  if (c->attn_tc && attention_tc_supported(p)) { LAUNCHED(c, launch_attention_tc(p, (cudaStream_t)stream), "attention_tc"); }
+  if (c->attn_tc && attention_tc_supported(p)) { LAUNCHED(c, launch_attention_tc(p, c->encode_tiled, (cudaStream_t)stream), "attention_tc"); }
   {
     // the mma.sync kernel keeps K and V^T (hi + lo) of one (batch, head) resident in shared memory
     const size_t need = attention_smem_bytes(p);

@@ -327,8 +327,16 @@ template <int D, int DT, bool SPLIT>
 static cudaError_t launch_attn_t(const AttnParams& p, cudaStream_t stream) {
   const size_t smem = attention_smem_bytes(p);
   auto kern = attention_kernel<D, DT, SPLIT>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
+  // the opt-in shared-memory ceiling is set once per (instantiation, device): not a stream operation, and not legal inside a
+  // CUDA-graph capture, so it must not ride on every launch
+  static int attr_smem[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if ((int)smem > attr_smem[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_smem[dev & 63] = (int)smem;
+  }
   dim3 grid(p.H, p.B);
   kern<<<grid, 256, smem, stream>>>(p);
   return cudaGetLastError();

@@ -1,17 +1,25 @@
-// tcgen05 attention for the decoder's hot shapes (head_dim 32, (hi, lo) operand pairs, no relative bias):
+// tcgen05 attention for the decoder's hot shapes (head_dim 32, (hi, lo) operand pairs, no relative bias), round-2 design:
 //
-//   one CTA per (batch, head, 128-query-row tile); keys stream through in chunks of 64.
-//   per chunk:  S[128x64]  = Q K^T          6 x tcgen05.mma (M128 N64 K16: hi*hi, lo*hi, hi*lo over head_dim 32), fp32 in TMEM
-//               thread r   = query row r:   tcgen05.ld its 64 scores, log2-domain scale / soft causal / key mask, online
-//                                           max + exp2 + row sum in registers, P -> (hi, lo) fp16 written to shared
-//                                           memory in the 128B-swizzled K-major layout the MMA reads
-//               Oc[128x32] = P V           12 x tcgen05.mma (M128 N32 K16) into a second TMEM region,
-//               o = o * corr + Oc           (running output kept in registers: no TMEM read-modify-write)
+//   one CTA per (batch, head, 128-query-row tile); keys stream through in chunks of 64.  Warps 0-3 = softmax (thread = query
+//   row = TMEM lane), warp 4 = control (one lane issues every TMA load and every MMA; the warp owns the TMEM allocation).
 //
-// Same mask semantics as attention.cu (reference components.py:51-80): the causal constant is the reference's soft -1e4,
-// key padding adds finfo.min, rows whose visible keys are all padded keep going past the diagonal.
-// Accumulators live in TMEM, so a thread needs ~100 registers instead of the mma.sync kernel's 128 and three CTAs fit
-// per SM (64 KB of shared memory, 128 TMEM columns each): one CTA's softmax overlaps the others' MMAs and loads.
+//   control lane, per chunk c:   QK(c+1):  S[128x64] = Q K^T         6 x tcgen05.mma M128 N64 K16 (hi*hi, lo*hi, hi*lo), as soon
+//                                          as the softmax warps have pulled S(c) into registers (s_free) -> S(c+1) is ready when
+//                                          they come back; TMA brings K(c+2) / V(c+1) in behind the MMAs that free their slots
+//                                PV(c):    O[128x32] += P V          12 x tcgen05.mma M128 N32 K16 once P(c) is in shared memory
+//   softmax thread, per chunk:   tcgen05.ld its 64 scores (ONE pass over TMEM: its 64 B/clk read port, MUFU and issue all top
+//                                out near 16 elements/clk/SM), max with FMNMX3, exp2 with the scale folded into a packed FFMA2,
+//                                (hi, lo) fp16 split, 128-bit stores into the 128B-swizzled K-major tile the MMA reads.
+//   O stays in TMEM for the whole key range: the running maximum is only raised when a chunk exceeds it by more than 2^8 (the
+//   row's O / l are then rescaled through tcgen05.ld/st), so P <= 256 fits fp16 and the per-chunk read-modify-write of O, its
+//   barrier round trip and the online-softmax correction of the round-1 kernel are gone.  The softmax warps never wait for an
+//   MMA they did not need: the only waits are "S(c) ready" and "P buffer free".
+//
+// Same mask semantics as attention.cu (reference components.py:51-80): the causal constant is the reference's soft -1e4, key
+// padding adds finfo.min, keys beyond Lk are excluded.  A causal tile first runs the chunks up to its diagonal; hidden keys have
+// weight exp(-1e4 - m) == 0 exactly in fp32 once m > -1e4 + 104, so stopping there is bit-compatible with the reference's
+// full-width softmax.  If some row has only seen padded keys by then (m still <= -9000), the tile is re-run over every chunk
+// with the exact formulas (rare: the first history slot is always valid in VIMA's data).
 #include "kernels.h"
 
 namespace vima {
@@ -22,16 +30,27 @@ constexpr float FP32_MIN_TC = -3.4028234663852886e38f;
 constexpr float LOG2E_TC = 1.4426950408889634f;
 constexpr float CAUSAL_L2_TC = -1e4f * LOG2E_TC;
 constexpr float EXIT_L2_TC = -9000.f * LOG2E_TC;
+constexpr float LAZY_THRESH = 8.0f;  // log2(256): raise the reference maximum only when a chunk beats it by more than this
 
-constexpr int ATC_THREADS = 160;  // warps 0-3: one query row per thread (TMEM lane = thread); warp 4: MMA issue + TMEM alloc
+constexpr int ATC_THREADS = 160;
 constexpr int ATC_BM = 128, ATC_KC = 64, ATC_D = 32;
-constexpr int ATC_TMEM_COLS = 128;  // S: columns [0, 64), O chunk: [64, 96)
-// shared memory carve (bytes, tile bases 1024-aligned)
-constexpr int OFF_QH = 0, OFF_QL = 8192, OFF_KH = 16384, OFF_KL = 20480, OFF_VH = 24576, OFF_VL = 28672, OFF_PH = 32768, OFF_PL = 49152;
-constexpr int OFF_MASK = 65536, OFF_BAR = OFF_MASK + 256, OFF_TPTR = OFF_BAR + 8, ATC_SMEM = OFF_TPTR + 8;
+constexpr int ATC_TMEM_COLS = 128;   // S: columns [0, 64), O: [64, 96)
+constexpr int ATC_MAX_LK = 512;      // mask row held in shared memory as floats
+// shared memory carve (bytes; swizzled tiles 1024-aligned)
+constexpr int OFF_QH = 0, OFF_QL = 8192;
+constexpr int OFF_K = 16384;                 // 2 stages x {hi 4096, lo 4096}
+constexpr int OFF_VH = 32768, OFF_VL = 36864;
+constexpr int OFF_PH = 40960, OFF_PL = 57344;
+constexpr int OFF_MASK = 73728;              // float[512]
+constexpr int OFF_FLAG = OFF_MASK + ATC_MAX_LK * 4;  // int[8]: per-chunk "any key masked"
+constexpr int OFF_BAR = OFF_FLAG + 32;       // 8 mbarriers
+constexpr int OFF_TPTR = OFF_BAR + 64;
+constexpr int ATC_SMEM = OFF_TPTR + 16;
 
-__device__ __forceinline__ uint32_t swz64(uint32_t o) { return o ^ (((o >> 7) & 3u) << 4); }    // 64-byte rows (SWIZZLE_64B)
-__device__ __forceinline__ uint32_t swz128(uint32_t o) { return o ^ (((o >> 7) & 7u) << 4); }   // 128-byte rows (SWIZZLE_128B)
+struct AttnTcParams {
+  AttnParams a;
+  CUtensorMap tm_q_hi, tm_q_lo, tm_k_hi, tm_k_lo, tm_v_hi, tm_v_lo;
+};
 
 __device__ __forceinline__ uint64_t desc_sw64(uint32_t a) {
   return (uint64_t)((a >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
@@ -40,42 +59,43 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t a) {
   return (uint64_t)((a >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
-// V is consumed as the MN-major B operand of P V: the chunk sits in shared memory exactly as it does in HBM (one 64-byte
-// row of head_dim per key, 64B swizzle) and needs no transpose.  SBO = stride between groups of 8 keys, one K=16 step = 1024 B.
-__device__ __forceinline__ uint64_t desc_sw64_mn(uint32_t a) {
-  return (uint64_t)((a >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+// (x0, x1) * s + n  as one packed FFMA2
+__device__ __forceinline__ void fma2(float& x0, float& x1, float s, float n) {
+  unsigned long long xx, ss, nn;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(xx) : "f"(x0), "f"(x1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(ss) : "f"(s));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(nn) : "f"(n));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(xx) : "l"(xx), "l"(ss), "l"(nn));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(xx));
 }
 
-__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc, bool valid) {  // !valid: 16 zero bytes
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(valid ? 16 : 0) : "memory");
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
+      "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]),
+      "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// rows [r0, r0 + n_rows) of a (hi, lo) operand pair, 64-byte head slices -> two 64B-swizzled tiles; rows >= r_end are zero
-__device__ __forceinline__ void stage_rows(uint32_t s_hi, uint32_t s_lo, const unsigned short* g_hi, const unsigned short* g_lo, size_t row0,
-                                           int ld, int col0, int n_rows, int r_valid, int t, int nt) {
-  for (int idx = t; idx < n_rows * 4; idx += nt) {
-    const int r = idx >> 2, c = idx & 3;
-    const bool ok = r < r_valid;
-    const size_t off = ok ? (row0 + r) * (size_t)ld + col0 + c * 8 : 0;
-    const uint32_t o = swz64((uint32_t)(r * 64 + c * 16));
-    cp_async16(s_hi + o, g_hi + off, ok);
-    cp_async16(s_lo + o, g_lo + off, ok);
-  }
-}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // one query row of the output: x = o * inv as (hi, lo) 16-bit pairs [+ e4m3 cross-term views for an "f16f8" consumer GEMM]
 template <int DT>
-__device__ __forceinline__ void store_row(const AttnParams& p, int b, int row, int h, const float (&o)[ATC_D], float inv) {
+__device__ __forceinline__ void store_row(const AttnParams& p, int b, int row, int h, const uint32_t (&o)[ATC_D], float inv) {
   const size_t off = ((size_t)b * p.Lq + row) * p.ldo + h * ATC_D;
 #pragma unroll
   for (int c8 = 0; c8 < ATC_D / 8; ++c8) {
     uint32_t hi[4], lo[4];
     float x[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) x[e] = o[c8 * 8 + e] * inv;
+    for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(o[c8 * 8 + e]) * inv;
 #pragma unroll
     for (int e = 0; e < 4; ++e) split2<DT>(x[2 * e], x[2 * e + 1], hi[e], lo[e]);
     *reinterpret_cast<uint4*>(p.o_hi + off + c8 * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -98,11 +118,19 @@ __device__ __forceinline__ void store_row(const AttnParams& p, int b, int row, i
 }
 
 template <int DT>
-__global__ void __launch_bounds__(ATC_THREADS, 3) attention_tc_kernel(const AttnParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* sm = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+__global__ void __launch_bounds__(ATC_THREADS, 3) attention_tc_kernel(const __grid_constant__ AttnTcParams P) {
+  const AttnParams& p = P.a;
+  extern __shared__ __align__(1024) uint8_t sm[];
   float* maskadd = reinterpret_cast<float*>(sm + OFF_MASK);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + OFF_BAR);
+  int* cflag = reinterpret_cast<int*>(sm + OFF_FLAG);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + OFF_BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;  // [2]
+  uint64_t* v_full = bars + 3;
+  uint64_t* s_full = bars + 4;  // QK(c) retired: S(c) readable
+  uint64_t* s_free = bars + 5;  // every active softmax warp has S(c) in registers
+  uint64_t* p_full = bars + 6;  // every active softmax warp has written P(c) (and finished any rescale of O)
+  uint64_t* p_free = bars + 7;  // PV(c) retired: P / V buffers reusable, O consistent
   uint32_t* tptr = reinterpret_cast<uint32_t*>(sm + OFF_TPTR);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -112,204 +140,279 @@ __global__ void __launch_bounds__(ATC_THREADS, 3) attention_tc_kernel(const Attn
   const int mld = p.mask_ld ? p.mask_ld : Lk;
   const int qp0 = p.q_pos0;
   const uint32_t sbase = smem_u32(sm);
-  const int n_chunks = (Lk + ATC_KC - 1) / ATC_KC;
+  const int rows_here = min(ATC_BM, Lq - q0);
+  const int n_act = (rows_here + 31) >> 5;  // softmax warps that own at least one real query row
+  const int n_all = (Lk + ATC_KC - 1) / ATC_KC;
+  int n_plan = n_all;  // causal: chunks up to the tile's diagonal
+  if (p.causal) {
+    const int last_key = min(Lk - 1, q0 + rows_here - 1 + qp0);
+    n_plan = last_key / ATC_KC + 1;
+  }
 
+  if ((sbase & 1023u) != 0u) {  // the swizzled tiles assume a 1024-byte aligned window (no static shared memory in this kernel)
+    if (tid == 0) printf("vima_b200: attention_tc shared memory window is not 1024-byte aligned\n");
+    __trap();
+  }
   if (warp == 4) {
     tmem_alloc<ATC_TMEM_COLS>(tptr);
     if (lane == 0) {
-      mbar_init(bar, 1);
+      mbar_init(q_full, 1);
+      mbar_init(&k_full[0], 1);
+      mbar_init(&k_full[1], 1);
+      mbar_init(v_full, 1);
+      mbar_init(s_full, 1);
+      mbar_init(s_free, (uint32_t)n_act);
+      mbar_init(p_full, (uint32_t)n_act);
+      mbar_init(p_free, 1);
       fence_barrier_init();
+      tma_prefetch_desc(&P.tm_q_hi); tma_prefetch_desc(&P.tm_q_lo);
+      tma_prefetch_desc(&P.tm_k_hi); tma_prefetch_desc(&P.tm_k_lo);
+      tma_prefetch_desc(&P.tm_v_hi); tma_prefetch_desc(&P.tm_v_lo);
     }
   }
-  // cp.async groups are committed in the order {Q, K0}, {V0}, then per chunk {K(ch+1)}, {V(ch+1)} (possibly empty), so
-  // "wait_group 1" always means: everything except the most recently committed group has landed.
-  // K / V chunk staging: thread t < 128 always copies the same two 16-byte slots (rows t/4 and t/4 + 32, 16-byte column t%4),
-  // so the global offsets and the swizzled shared-memory offsets are computed once.
-  const int ld_r = (tid >> 2) & 31, ld_c = tid & 3;
-  const uint32_t ld_so = swz64((uint32_t)(ld_r * 64 + ld_c * 16));  // row + 32 lands 2048 bytes further (same swizzle phase)
-  const size_t kv_row0 = (size_t)b * kvb + ld_r;
-  const size_t k_off0 = kv_row0 * p.ldk + h * ATC_D + ld_c * 8, v_off0 = kv_row0 * p.ldv + h * ATC_D + ld_c * 8;
-  auto load_chunk = [&](uint32_t s_hi, uint32_t s_lo, const unsigned short* g_hi, const unsigned short* g_lo, size_t off0, int ld, int ch) {
-    if (warp < 4 && ch < n_chunks) {
-      const int rem = Lk - ch * ATC_KC;
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const bool ok = ld_r + 32 * i < rem;
-        const size_t off = ok ? off0 + (size_t)(ch * ATC_KC + 32 * i) * ld : 0;
-        cp_async16(s_hi + ld_so + 2048 * i, g_hi + off, ok);
-        cp_async16(s_lo + ld_so + 2048 * i, g_lo + off, ok);
-      }
-    }
-    cp_async_commit();
-  };
-  auto load_k = [&](int ch) { load_chunk(sbase + OFF_KH, sbase + OFF_KL, p.k_hi, p.k_lo, k_off0, p.ldk, ch); };
-  auto load_v = [&](int ch) { load_chunk(sbase + OFF_VH, sbase + OFF_VL, p.v_hi, p.v_lo, v_off0, p.ldv, ch); };
-  if (warp < 4) stage_rows(sbase + OFF_QH, sbase + OFF_QL, p.q_hi, p.q_lo, (size_t)b * Lq + q0, p.ldq, h * ATC_D, ATC_BM, Lq - q0, tid, 128);
-  load_k(0);
-  load_v(0);
+  if (tid < 8) cflag[tid] = 0;
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = *tptr;
-  const uint32_t t_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);  // this warp's TMEM lane quadrant (warps 0-3)
 
   const uint32_t fmt = (DT == DT_BF16) ? 1u : 0u;
   const uint32_t idesc_s = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(ATC_KC >> 3) << 17) | ((uint32_t)(ATC_BM >> 4) << 24);
   const uint32_t idesc_o = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 16) | ((uint32_t)(ATC_D >> 3) << 17) | ((uint32_t)(ATC_BM >> 4) << 24);
+  const int x_col = h * ATC_D;  // element column of this head inside the q / k / v row
+  const int kv_row0 = b * kvb;
 
-  const float c_l2 = p.scale * LOG2E_TC;
-  const int row = q0 + tid;  // meaningful for tid < 128
-  // A warp whose 32 query rows all lie past Lq (the 7-row last tile of a 263-token history) only helps with the copies and
-  // barriers: its P rows stay whatever shared memory holds, which only feeds output rows nobody stores.
-  const bool w_on = warp < 4 && (q0 + warp * 32 < Lq);
-  float m_run = -INFINITY, l_run = 0.f;
-  float o_acc[ATC_D];
+  if (warp == 4) {
+    // =============================== control lane: TMA loads + MMA issue ===============================
+    if (lane == 0) {
+      uint32_t g = 0;                 // chunks issued so far (both passes): parity of s_* / p_* / v_full
+      uint32_t k_use[2] = {0u, 0u};   // completed fills of each K stage
+      auto load_k = [&](int c, int stage) {
+        uint8_t* dst = sm + OFF_K + stage * 8192;
+        mbar_arrive_expect_tx(&k_full[stage], 8192u);
+        tma_load_2d(dst, &P.tm_k_hi, &k_full[stage], x_col, kv_row0 + c * ATC_KC);
+        tma_load_2d(dst + 4096, &P.tm_k_lo, &k_full[stage], x_col, kv_row0 + c * ATC_KC);
+      };
+      auto load_v = [&](int c) {
+        mbar_arrive_expect_tx(v_full, 8192u);
+        tma_load_2d(sm + OFF_VH, &P.tm_v_hi, v_full, x_col, kv_row0 + c * ATC_KC);
+        tma_load_2d(sm + OFF_VL, &P.tm_v_lo, v_full, x_col, kv_row0 + c * ATC_KC);
+      };
+      auto issue_qk = [&](int c, uint32_t gg) {  // gg = global index of chunk c
+        const int stage = c & 1;
+        mbar_wait(&k_full[stage], k_use[stage] & 1u);
+        k_use[stage]++;
+        if (gg > 0) mbar_wait(s_free, (gg - 1) & 1u);  // S(previous chunk) has been read out
+        tcgen05_fence_after();
+        const uint64_t dqh = desc_sw64(sbase + OFF_QH), dql = desc_sw64(sbase + OFF_QL);
+        const uint64_t dkh = desc_sw64(sbase + OFF_K + stage * 8192), dkl = desc_sw64(sbase + OFF_K + stage * 8192 + 4096);
 #pragma unroll
-  for (int i = 0; i < ATC_D; ++i) o_acc[i] = 0.f;
-  uint32_t phase = 0;
-
-  for (int ch = 0; ch < n_chunks; ++ch) {
-    const int k0 = ch * ATC_KC;
-    // Past the diagonal the tile may stop after this chunk: no prefetch then (a CTA must not exit with copies in flight).
-    const bool may_exit = p.causal && (k0 + ATC_KC > q0 + ATC_BM - 1 + qp0);
-    int masked = 0;
-    if (tid < ATC_KC) {
-      float mk = -INFINITY;  // beyond the sequence: excluded
-      const int j = k0 + tid;
-      if (j < Lk) mk = (p.key_mask == nullptr || p.key_mask[(size_t)b * mld + j]) ? 0.f : FP32_MIN_TC;
-      maskadd[tid] = mk;
-      masked = mk != 0.f;
-    }
-    cp_async_wait<1>();   // K(ch) (and Q) landed; V(ch) may still be in flight
-    fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
-    tcgen05_fence_before();
-    const int any_masked = __syncthreads_or(masked);
-    // ---- S = Q K^T ----
-    if (warp == 4 && lane == 0) {
-      tcgen05_fence_after();
-      const uint64_t dqh = desc_sw64(sbase + OFF_QH), dql = desc_sw64(sbase + OFF_QL);
-      const uint64_t dkh = desc_sw64(sbase + OFF_KH), dkl = desc_sw64(sbase + OFF_KL);
+        for (int k = 0; k < ATC_D / 16; ++k) umma_f16(tmem, dqh + 2 * k, dkh + 2 * k, idesc_s, (uint32_t)(k != 0));
 #pragma unroll
-      for (int k = 0; k < ATC_D / 16; ++k) umma_f16(tmem, dqh + 2 * k, dkh + 2 * k, idesc_s, (uint32_t)(k != 0));
+        for (int k = 0; k < ATC_D / 16; ++k) umma_f16(tmem, dql + 2 * k, dkh + 2 * k, idesc_s, 1u);
 #pragma unroll
-      for (int k = 0; k < ATC_D / 16; ++k) umma_f16(tmem, dql + 2 * k, dkh + 2 * k, idesc_s, 1u);
+        for (int k = 0; k < ATC_D / 16; ++k) umma_f16(tmem, dqh + 2 * k, dkl + 2 * k, idesc_s, 1u);
+        umma_commit(s_full);
+      };
+      mbar_arrive_expect_tx(q_full, 16384u);
+      tma_load_2d(sm + OFF_QH, &P.tm_q_hi, q_full, x_col, b * Lq + q0);
+      tma_load_2d(sm + OFF_QL, &P.tm_q_lo, q_full, x_col, b * Lq + q0);
+      int n = n_plan;
+      for (int pass = 0; pass < 2; ++pass) {
+        load_k(0, 0);
+        if (n > 1) load_k(1, 1);
+        load_v(0);
+        if (pass == 0) mbar_wait(q_full, 0);
+        issue_qk(0, g);
+        for (int c = 0; c < n; ++c, ++g) {
+          if (c + 1 < n) issue_qk(c + 1, g + 1);
+          mbar_wait(p_full, g & 1u);
+          mbar_wait(v_full, g & 1u);
+          tcgen05_fence_after();
+          {
+            const uint64_t dph = desc_sw128(sbase + OFF_PH), dpl = desc_sw128(sbase + OFF_PL);
+            const uint64_t dvh = desc_sw64(sbase + OFF_VH), dvl = desc_sw64(sbase + OFF_VL);  // MN-major B: one 64-byte row per key
+            const uint32_t t_o = tmem + 64;
 #pragma unroll
-      for (int k = 0; k < ATC_D / 16; ++k) umma_f16(tmem, dqh + 2 * k, dkl + 2 * k, idesc_s, 1u);
-      umma_commit(bar);
-    }
-    float corr = 1.f;
-    if (warp < 4) {
-      mbar_wait(bar, phase);
-      phase ^= 1;
-      tcgen05_fence_after();
-      if (!may_exit) load_k(ch + 1); else cp_async_commit();  // the K tile is free once the MMAs above have retired
-    }
-    if (w_on) {
-      uint32_t sv[ATC_KC];
-      tmem_ld_32x32(t_row, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
-      tmem_ld_32x32(t_row + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
-      tmem_ld_wait();
-      const bool needs_causal = p.causal && (k0 + ATC_KC - 1 > q0 + qp0);
-      float mx = -INFINITY, neg_m;
-      float sc;  // p = exp2(sv * sc - m_new)
-      if (!any_masked && !needs_causal) {  // plain chunk: the scale rides in the exponent FMA
+            for (int k = 0; k < ATC_KC / 16; ++k) umma_f16(t_o, dph + 2 * k, dvh + 64 * k, idesc_o, (uint32_t)((c | k) != 0));
 #pragma unroll
-        for (int c = 0; c < ATC_KC; ++c) mx = fmaxf(mx, __uint_as_float(sv[c]));
-        mx *= c_l2;
-        sc = c_l2;
-      } else {
-        const int thr = row + qp0 - k0;  // key column c of this chunk is causally hidden iff c > thr
+            for (int k = 0; k < ATC_KC / 16; ++k) umma_f16(t_o, dpl + 2 * k, dvh + 64 * k, idesc_o, 1u);
 #pragma unroll
-        for (int c4 = 0; c4 < ATC_KC; c4 += 4) {
-          const float4 m4 = *reinterpret_cast<const float4*>(maskadd + c4);
-          const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float y = fmaf(__uint_as_float(sv[c4 + e]), c_l2, mm[e]);
-            if (needs_causal && c4 + e > thr) y = CAUSAL_L2_TC + mm[e];
-            sv[c4 + e] = __float_as_uint(y);
-            mx = fmaxf(mx, y);
+            for (int k = 0; k < ATC_KC / 16; ++k) umma_f16(t_o, dph + 2 * k, dvl + 64 * k, idesc_o, 1u);
           }
+          umma_commit(p_free);
+          mbar_wait(p_free, g & 1u);  // PV(c) -- and with it QK(c), QK(c+1) -- retired: their operand slots are free
+          if (c + 2 < n) load_k(c + 2, c & 1);
+          if (c + 1 < n) load_v(c + 1);
         }
-        sc = 1.f;
+        // every row past the causal range must have seen a valid key; otherwise the whole tile is redone over all chunks
+        if (pass == 1 || !(p.causal && n_plan < n_all)) break;
+        if (!__syncthreads_or(0)) break;  // (vote of the softmax warps; this lane only joins the barrier)
+        n = n_all;
       }
-      const float m_new = fmaxf(m_run, mx);
-      corr = ex2_approx(m_run - m_new);
-      m_run = m_new;
-      neg_m = -m_new;
-      float ps = 0.f;
-      // P -> (hi, lo) 16-bit pairs, row `tid` of the 128x64 K-major tile (128-byte rows, 128B swizzle)
+    } else {
+      // the other lanes of the control warp only join the block-wide vote (same trip count as lane 0)
+      if (p.causal && n_plan < n_all) __syncthreads_or(0);
+    }
+  } else {
+    // ======================================= softmax warps =======================================
+    // key mask row of this batch element as additive terms; per-chunk "has masked keys" flags
+    for (int j = tid; j < n_all * ATC_KC; j += 128) {
+      float mk = -INFINITY;  // beyond the sequence: excluded
+      if (j < Lk) mk = (p.key_mask == nullptr || p.key_mask[(size_t)b * mld + j]) ? 0.f : FP32_MIN_TC;
+      maskadd[j] = mk;
+      if (mk != 0.f) atomicOr(&cflag[j >> 6], 1);
+    }
+    named_bar_sync(1, 128);
+    const bool w_on = warp < n_act;
+    const int row = q0 + tid;
+    const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
+    const float c_l2 = p.scale * LOG2E_TC;
+    const int rpos = row + qp0;                       // this row's key position (causal)
+    const int wpos_min = q0 + warp * 32 + qp0;        // smallest / largest key position among the warp's rows
+    const int wpos_max = wpos_min + 31;
+    // this thread's P row: 8 x 16-byte slots, 128B swizzle (slot ^ (row & 7))
+    uint32_t pslot[8];
 #pragma unroll
-      for (int c8 = 0; c8 < ATC_KC / 8; ++c8) {
-        uint32_t hi[4], lo[4];
+    for (int c8 = 0; c8 < 8; ++c8) pslot[c8] = sbase + OFF_PH + (uint32_t)tid * 128u + (uint32_t)((c8 ^ (tid & 7)) << 4);
+    float m_ref = -INFINITY, l_run = 0.f;
+    uint32_t g = 0;
+    int n = n_plan;
+    for (int pass = 0; pass < 2; ++pass) {
+      const bool full = pass == 1;
+      if (full) { m_ref = -INFINITY; l_run = 0.f; }
+      if (w_on) {
+        for (int c = 0; c < n; ++c, ++g) {
+          const int k0 = c * ATC_KC;
+          const bool hidden = p.causal && !full && k0 > wpos_max;  // every key of the chunk is causally hidden from this warp
+          mbar_wait(s_full, g & 1u);
+          tcgen05_fence_after();
+          uint32_t ph[ATC_KC / 2], pl[ATC_KC / 2];
+          float ps = 0.f, m_use = m_ref;
+          bool grow = false;
+          if (!hidden) {
+            uint32_t sv[ATC_KC];
+            tmem_ld_32x32(t_row, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+            tmem_ld_32x32(t_row + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+            tmem_ld_wait();
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_free);
+            const bool needs_causal = p.causal && (k0 + ATC_KC - 1 > wpos_min);
+            float mx, sc;
+            if (!needs_causal && !cflag[c]) {  // plain chunk: the scale rides in the exponent FMA
+              float m0 = __uint_as_float(sv[0]), m1 = __uint_as_float(sv[1]);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(sv[c8 * 8 + 2 * e]), sc, neg_m));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(sv[c8 * 8 + 2 * e + 1]), sc, neg_m));
-          ps += p0 + p1;
-          split2<DT>(p0, p1, hi[e], lo[e]);
+              for (int i = 2; i < ATC_KC; i += 4) {
+                m0 = max3(m0, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
+                if (i + 3 < ATC_KC) m1 = max3(m1, __uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3]));
+              }
+              mx = fmaxf(m0, m1) * c_l2;
+              sc = c_l2;
+            } else {
+              mx = -INFINITY;
+#pragma unroll
+              for (int c4 = 0; c4 < ATC_KC; c4 += 4) {
+                const float4 m4 = *reinterpret_cast<const float4*>(maskadd + k0 + c4);
+                const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float y = fmaf(__uint_as_float(sv[c4 + e]), c_l2, mm[e]);
+                  if (p.causal && k0 + c4 + e > rpos) y = CAUSAL_L2_TC + mm[e];
+                  sv[c4 + e] = __float_as_uint(y);
+                  mx = fmaxf(mx, y);
+                }
+              }
+              sc = 1.f;
+            }
+            grow = mx > m_ref + LAZY_THRESH;  // also the first chunk (m_ref = -inf)
+            if (grow) m_use = mx;
+            const float neg_m = -m_use;
+            float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < ATC_KC / 2; ++i) {
+              float x0 = __uint_as_float(sv[2 * i]), x1 = __uint_as_float(sv[2 * i + 1]);
+              fma2(x0, x1, sc, neg_m);
+              const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+              ps0 += p0;
+              ps1 += p1;
+              split2<DT>(p0, p1, ph[i], pl[i]);
+            }
+            ps = ps0 + ps1;
+          } else {
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_free);
+#pragma unroll
+            for (int i = 0; i < ATC_KC / 2; ++i) { ph[i] = 0u; pl[i] = 0u; }
+          }
+          // the P buffer is free and O is quiescent once PV of the previous chunk has retired
+          if (g > 0) mbar_wait(p_free, (g - 1) & 1u);
+          // raise the reference maximum of the rows that need it: O and l carry exp2(-m_ref)
+          float f = 1.f;
+          if (grow && c > 0) f = ex2_approx(m_ref - m_use);
+          if (c > 0 && __any_sync(0xffffffffu, grow)) {
+            uint32_t ov[ATC_D];
+            tcgen05_fence_after();
+            tmem_ld_32x32(t_row + 64, ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < ATC_D; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * f);
+            tmem_st_32x32(t_row + 64, ov);
+            tmem_st_wait();
+          }
+          l_run = (c > 0 ? l_run * f : 0.f) + ps;
+          m_ref = m_use;
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8) {
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pslot[c8]), "r"(ph[4 * c8]), "r"(ph[4 * c8 + 1]), "r"(ph[4 * c8 + 2]),
+                         "r"(ph[4 * c8 + 3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pslot[c8] + (uint32_t)(OFF_PL - OFF_PH)), "r"(pl[4 * c8]),
+                         "r"(pl[4 * c8 + 1]), "r"(pl[4 * c8 + 2]), "r"(pl[4 * c8 + 3]) : "memory");
+          }
+          fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(p_full);
         }
-        const uint32_t o = swz128((uint32_t)(tid * 128 + c8 * 16));
-        *reinterpret_cast<uint4*>(sm + OFF_PH + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(sm + OFF_PL + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        mbar_wait(p_free, (g - 1) & 1u);  // the last PV has retired: O is complete
+        tcgen05_fence_after();
       }
-      l_run = l_run * corr + ps;
+      if (pass == 1 || !(p.causal && n_plan < n_all)) break;
+      const int undone = w_on && row < Lq && !(m_ref > EXIT_L2_TC);
+      if (!__syncthreads_or(undone)) break;
+      n = n_all;
     }
-    if (warp < 4) {
-      cp_async_wait<1>();  // V(ch) landed (K(ch+1) may still be in flight)
-      fence_proxy_async();
-      tcgen05_fence_before();
-    }
-    __syncthreads();
-    // ---- O chunk = P V ----
-    if (warp == 4 && lane == 0) {
-      tcgen05_fence_after();
-      const uint64_t dph = desc_sw128(sbase + OFF_PH), dpl = desc_sw128(sbase + OFF_PL);
-      const uint64_t dvh = desc_sw64_mn(sbase + OFF_VH), dvl = desc_sw64_mn(sbase + OFF_VL);
-      const uint32_t t_o = tmem + 64;
-#pragma unroll
-      for (int k = 0; k < ATC_KC / 16; ++k) umma_f16(t_o, dph + 2 * k, dvh + 64 * k, idesc_o, (uint32_t)(k != 0));
-#pragma unroll
-      for (int k = 0; k < ATC_KC / 16; ++k) umma_f16(t_o, dpl + 2 * k, dvh + 64 * k, idesc_o, 1u);
-#pragma unroll
-      for (int k = 0; k < ATC_KC / 16; ++k) umma_f16(t_o, dph + 2 * k, dvl + 64 * k, idesc_o, 1u);
-      umma_commit(bar);
-    }
-    int done = 1;
-    if (warp < 4) {
-      mbar_wait(bar, phase);
-      phase ^= 1;
-      tcgen05_fence_after();
-      if (!may_exit) load_v(ch + 1); else cp_async_commit();  // the V tile is free once P V has retired
-    }
+    // ---- normalise and store (hi, lo) [+ e4m3 views] ----
     if (w_on) {
       uint32_t ov[ATC_D];
       tmem_ld_32x32(t_row + 64, ov);
       tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < ATC_D; ++i) o_acc[i] = fmaf(o_acc[i], corr, __uint_as_float(ov[i]));
-      tcgen05_fence_before();
-      done = (row >= Lq) || (m_run > EXIT_L2_TC);
-    }
-    // Every later chunk is causally hidden for all rows of this tile: its weights are exp(-1e4 - m) == 0 in fp32 once
-    // m > -1e4 + 104, so stopping is bit-identical to the reference's full-width softmax (rows that have only seen padded keys
-    // keep going).  Otherwise no barrier is needed here: the two barriers of the next chunk order every reuse.
-    if (may_exit) {
-      if (__syncthreads_and(done)) break;
-      load_k(ch + 1);
-      load_v(ch + 1);
+      if (row < Lq) store_row<DT>(p, b, row, h, ov, 1.0f / l_run);
     }
   }
-  cp_async_wait<0>();
-
-  // ---- normalise and store (hi, lo) [+ e4m3 views] ----
-  if (warp < 4 && row < Lq) store_row<DT>(p, b, row, h, o_acc, 1.0f / l_run);
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 4) {
     tcgen05_fence_after();
     tmem_dealloc<ATC_TMEM_COLS>(tmem);
   }
+}
+
+typedef CUresult (*PFN_encodeTiled_attn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// [rows, H*32] 16-bit view of one operand (row pitch ld elements), boxes of box_rows x 32 elements (64 bytes), 64B swizzle
+static bool make_map(void* encode, CUtensorMap* tm, const void* base, int dtype, long long rows, int cols, int ld, int box_rows) {
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)ATC_D, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapDataType dt = dtype == DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  return ((PFN_encodeTiled_attn)encode)(tm, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace
@@ -320,23 +423,37 @@ bool attention_tc_supported(const AttnParams& p) {
   if (!(al(p.q_hi) && al(p.q_lo) && al(p.k_hi) && al(p.k_lo) && al(p.v_hi) && al(p.v_lo) && al(p.o_hi) && al(p.o_lo) && al(p.o_lo8) && al(p.o_hi8)))
     return false;
   return p.D == 32 && p.split != 0 && p.rel_bias == nullptr && p.q_lo && p.k_lo && p.v_lo && (p.ldq % 8 == 0) && (p.ldk % 8 == 0) &&
-         (p.ldv % 8 == 0) && (p.ldo % 8 == 0) && (p.o_lo8 == nullptr || p.ldo8 % 8 == 0) && p.H <= 65535 && p.B <= 65535;
+         (p.ldv % 8 == 0) && (p.ldo % 8 == 0) && (p.o_lo8 == nullptr || p.ldo8 % 8 == 0) && p.H <= 65535 && p.B <= 65535 && p.Lk >= 1 &&
+         p.Lk <= ATC_MAX_LK;
 }
 
-cudaError_t launch_attention_tc(const AttnParams& p, cudaStream_t stream) {
+cudaError_t launch_attention_tc(const AttnParams& p, void* encode_fn, cudaStream_t stream) {
   if (p.B == 0 || p.Lq == 0) return cudaSuccess;
+  AttnTcParams P;
+  P.a = p;
+  const int kvb = p.kv_batch_rows ? p.kv_batch_rows : p.Lk;
+  const int cols = p.H * ATC_D;
+  bool ok = make_map(encode_fn, &P.tm_q_hi, p.q_hi, p.dtype, (long long)p.B * p.Lq, cols, p.ldq, ATC_BM) &&
+            make_map(encode_fn, &P.tm_q_lo, p.q_lo, p.dtype, (long long)p.B * p.Lq, cols, p.ldq, ATC_BM) &&
+            make_map(encode_fn, &P.tm_k_hi, p.k_hi, p.dtype, (long long)p.B * kvb, cols, p.ldk, ATC_KC) &&
+            make_map(encode_fn, &P.tm_k_lo, p.k_lo, p.dtype, (long long)p.B * kvb, cols, p.ldk, ATC_KC) &&
+            make_map(encode_fn, &P.tm_v_hi, p.v_hi, p.dtype, (long long)p.B * kvb, cols, p.ldv, ATC_KC) &&
+            make_map(encode_fn, &P.tm_v_lo, p.v_lo, p.dtype, (long long)p.B * kvb, cols, p.ldv, ATC_KC);
+  if (!ok) return cudaErrorInvalidValue;
   dim3 grid((p.Lq + ATC_BM - 1) / ATC_BM, p.H, p.B);
-  const size_t smem = ATC_SMEM + 1024;
-  cudaError_t e;
-  if (p.dtype == DT_BF16) {
-    auto kern = attention_tc_kernel<DT_BF16>;
-    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-    kern<<<grid, ATC_THREADS, smem, stream>>>(p);
-  } else {
-    auto kern = attention_tc_kernel<DT_F16>;
-    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-    kern<<<grid, ATC_THREADS, smem, stream>>>(p);
+  const size_t smem = ATC_SMEM;
+  static bool attr_set[2][64] = {};  // once per (format, device): not legal inside a CUDA-graph capture
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int fi = p.dtype == DT_BF16 ? 1 : 0;
+  if (!attr_set[fi][dev & 63]) {
+    cudaError_t e = fi ? cudaFuncSetAttribute(attention_tc_kernel<DT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                       : cudaFuncSetAttribute(attention_tc_kernel<DT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set[fi][dev & 63] = true;
   }
+  if (fi) attention_tc_kernel<DT_BF16><<<grid, ATC_THREADS, smem, stream>>>(P);
+  else attention_tc_kernel<DT_F16><<<grid, ATC_THREADS, smem, stream>>>(P);
   return cudaGetLastError();
 }
 

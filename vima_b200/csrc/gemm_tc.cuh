@@ -53,16 +53,34 @@ struct alignas(64) GemmParams {
   unsigned char* out_lo8; // fp8 cross-term views of the output (mode-2 consumers), or null
   unsigned char* out_hi8;
   int ld_o8;
+  // LayerNorm folded into the GEMM: A holds the un-normalised rows, B holds W*gamma, and the epilogue applies
+  //   v = rstd[row] * (acc*acc_scale - mean[row]*ln_c1[col]) + bias[col]        (bias already contains W*beta)
+  const float* row_stats;  // fp32 [M, 2] = (mean, rstd), or null
+  const float* ln_c1;      // fp32 [N] in accumulator-column order: sum_k (W*gamma)[col, k]
+  int ln_cols;             // 1: every accumulator column, 2: only the value half of each GLU tile
+  // residual rows LayerNorm'd on the fly: r = (residual - mean[row]) * rstd[row] * res_gamma[col] + res_beta[col]
+  const float* res_stats;  // fp32 [M, 2], or null
+  const float* res_gamma;  // fp32 [Nout]
+  const float* res_beta;
+  // per-row partial sums (sum, sum of squares) of the stored output over this (n-tile, epilogue-half)'s columns
+  float* stats_out;        // fp32 [M, stats_parts, 2], or null
+  int stats_parts;         // = 2 * tiles_n
 };
 
 // Compile-time epilogue description. GENERIC: every flag is read from GemmParams at run time instead.
-template <bool GENERIC_, int ACT_, bool GLU_, bool MUL_, bool RES_, bool O32_, bool O16_, int DT_>
+template <bool GENERIC_, int ACT_, bool GLU_, bool MUL_, bool RES_, bool O32_, bool O16_, int DT_, bool LNA_ = false, bool LNR_ = false,
+          bool STATS_ = false>
 struct EpiCfg {
   static constexpr bool GENERIC = GENERIC_;
   static constexpr int ACT = ACT_;
   static constexpr bool GLU = GLU_, MUL = MUL_, RES = RES_, O32 = O32_, O16 = O16_;
   static constexpr int DT = DT_;
+  static constexpr bool LNA = LNA_;      // LayerNorm of the A operand folded in (row_stats, ln_c1)
+  static constexpr bool LNR = LNR_;      // residual rows LayerNorm'd on the fly (res_stats, res_gamma, res_beta)
+  static constexpr bool STATS = STATS_;  // emit per-row partial (sum, sum of squares) of the output
 };
+
+constexpr int GEMM_COLVEC_PLANES = 4;  // per accumulator buffer: bias | ln_c1 | res_gamma | res_beta, 256 floats each
 
 __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
   // start address [0,14) (>>4) | LBO [16,30) (ignored for swizzled K-major; 1) | SBO [32,46) = 8 rows * 128 B
@@ -98,9 +116,38 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_ro
   const bool has_res = E::GENERIC ? (p.residual != nullptr) : E::RES;
   const bool o32 = E::GENERIC ? (p.out_f32 != nullptr) : E::O32;
   const bool o16 = E::GENERIC ? (p.out_hi != nullptr) : E::O16;
+  const bool lna = E::GENERIC ? (p.row_stats != nullptr) : E::LNA;
+  const bool lnr = E::GENERIC ? (p.res_stats != nullptr) : E::LNR;
+  const bool stats = E::GENERIC ? (p.stats_out != nullptr) : E::STATS;
   const float scale = p.acc_scale;
   const int sub = lane >> 2;        // row within a group of 8
   const int kc = lane & 3;          // which 4-column group of the 16-column sub-chunk
+  const float* sc1 = sb + 256;      // ln_c1 tile (accumulator-column order, like the bias tile)
+  const float* sgam = sb + 512;     // res_gamma / res_beta tiles (output-column order)
+  const float* sbet = sb + 768;
+  // folded LayerNorm of the A rows: this thread's accumulator row is `row_base + lane`
+  float a_mean = 0.f, a_rstd = 1.f;
+  if (lna) {
+    const int row = row_base + lane;
+    if (row < p.M) {
+      const float2 ms = __ldg(reinterpret_cast<const float2*>(p.row_stats) + row);
+      a_mean = ms.x; a_rstd = ms.y;
+    }
+  }
+  const bool ln_gate = lna && p.ln_cols == 1;
+  // on-the-fly LayerNorm of the residual rows / partial output statistics: rows it*8 + sub of the transposed layout
+  float r_mean[4], r_rstd[4], st1[4], st2[4];
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    r_mean[it] = 0.f; r_rstd[it] = 1.f; st1[it] = 0.f; st2[it] = 0.f;
+    if (lnr) {
+      const int row = row_base + it * 8 + sub;
+      if (row < p.M) {
+        const float2 ms = __ldg(reinterpret_cast<const float2*>(p.res_stats) + row);
+        r_mean[it] = ms.x; r_rstd[it] = ms.y;
+      }
+    }
+  }
   for (int j0 = ehalf * 32; j0 < bn_out; j0 += 64) {
 #pragma unroll 1
     for (int j = j0; j < j0 + 32; j += 16) {
@@ -127,10 +174,28 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_ro
           const float4 b2 = *reinterpret_cast<const float4*>(sb + bn_out + j + i);
           const float bb1[4] = {b1.x, b1.y, b1.z, b1.w}, bb2[4] = {b2.x, b2.y, b2.z, b2.w};
 #pragma unroll
+          float cc1[4] = {0.f, 0.f, 0.f, 0.f}, cc2[4] = {0.f, 0.f, 0.f, 0.f};
+          if (lna) {
+            const float4 c1 = *reinterpret_cast<const float4*>(sc1 + j + i);
+            cc1[0] = c1.x; cc1[1] = c1.y; cc1[2] = c1.z; cc1[3] = c1.w;
+            if (ln_gate) {
+              const float4 c2 = *reinterpret_cast<const float4*>(sc1 + bn_out + j + i);
+              cc2[0] = c2.x; cc2[1] = c2.y; cc2[2] = c2.z; cc2[3] = c2.w;
+            }
+          }
+#pragma unroll
           for (int q = 0; q < 4; ++q) {
-            float a = fmaf(__uint_as_float(v[i + q]), scale, bb1[q]);
+            float a, gt;
+            if (lna) {
+              a = fmaf(fmaf(-a_mean, cc1[q], __uint_as_float(v[i + q]) * scale), a_rstd, bb1[q]);
+              gt = ln_gate ? fmaf(fmaf(-a_mean, cc2[q], __uint_as_float(g[i + q]) * scale), a_rstd, bb2[q])
+                           : fmaf(__uint_as_float(g[i + q]), scale, bb2[q]);
+            } else {
+              a = fmaf(__uint_as_float(v[i + q]), scale, bb1[q]);
+              gt = fmaf(__uint_as_float(g[i + q]), scale, bb2[q]);
+            }
             a = E::GENERIC ? apply_act(p.act, a) : act_ct<E::ACT>(a);
-            x[i + q] = a * fmaf(__uint_as_float(g[i + q]), scale, bb2[q]);
+            x[i + q] = a * gt;
           }
         }
       } else {
@@ -140,8 +205,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_ro
           const float4 b1 = *reinterpret_cast<const float4*>(sb + j + i);
           const float bb1[4] = {b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
+          float cc1[4] = {0.f, 0.f, 0.f, 0.f};
+          if (lna) {
+            const float4 c1 = *reinterpret_cast<const float4*>(sc1 + j + i);
+            cc1[0] = c1.x; cc1[1] = c1.y; cc1[2] = c1.z; cc1[3] = c1.w;
+          }
+#pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float a = fmaf(__uint_as_float(v[i + q]), scale, bb1[q]);
+            const float a = lna ? fmaf(fmaf(-a_mean, cc1[q], __uint_as_float(v[i + q]) * scale), a_rstd, bb1[q])
+                                : fmaf(__uint_as_float(v[i + q]), scale, bb1[q]);
             x[i + q] = E::GENERIC ? apply_act(p.act, a) : act_ct<E::ACT>(a);
           }
         }
@@ -163,7 +235,21 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_ro
         if (!(col_ok && row < p.M)) continue;
         float4 o = y[it];
         if (has_mul) { o.x *= mm[it].x; o.y *= mm[it].y; o.z *= mm[it].z; o.w *= mm[it].w; }
-        if (has_res) { o.x += rr[it].x; o.y += rr[it].y; o.z += rr[it].z; o.w += rr[it].w; }
+        if (has_res) {
+          float4 r = rr[it];
+          if (lnr) {
+            const float4 gm = *reinterpret_cast<const float4*>(sgam + j + kc * 4);
+            const float4 bt = *reinterpret_cast<const float4*>(sbet + j + kc * 4);
+            const float m_ = r_mean[it], s_ = r_rstd[it];
+            r.x = fmaf((r.x - m_) * s_, gm.x, bt.x); r.y = fmaf((r.y - m_) * s_, gm.y, bt.y);
+            r.z = fmaf((r.z - m_) * s_, gm.z, bt.z); r.w = fmaf((r.w - m_) * s_, gm.w, bt.w);
+          }
+          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        if (stats) {
+          st1[it] += (o.x + o.y) + (o.z + o.w);
+          st2[it] += fmaf(o.x, o.x, o.y * o.y) + fmaf(o.z, o.z, o.w * o.w);
+        }
         if (o32) *reinterpret_cast<float4*>(p.out_f32 + (size_t)row * p.ld_o32 + col) = o;
         if (o16) {
           if (p.out_lo8) {  // fp16 hi + e4m3 cross-term views for an "f16f8" consumer
@@ -188,6 +274,19 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_ro
       __syncwarp();
     }
   }
+  if (stats) {
+    // every row's 4 column-group lanes hold partial sums over this warp's chunks: fold them (fixed order -> run-to-run and
+    // batch-slice deterministic) and let the kc == 0 lane write the (n-tile, epilogue-half) partial
+    const int part = tn * 2 + ehalf;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      float s1 = st1[it], s2 = st2[it];
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 2); s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+      const int row = row_base + it * 8 + sub;
+      if (kc == 0 && row < p.M) reinterpret_cast<float2*>(p.stats_out)[(size_t)row * p.stats_parts + part] = make_float2(s1, s2);
+    }
+  }
 }
 
 // TWO_CTA instantiations contain cta_group::2 instructions and MUST be launched as 2-CTA clusters; the others run as single
@@ -204,8 +303,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   const int stage_bytes = (GEMM_A_TILE_BYTES + b_tile_bytes) * n_parts;
   uint8_t* stages = smem;
   float* staging = (float*)(smem + (size_t)p.n_stages * stage_bytes);
-  float* sbias = staging + GEMM_STAGING_BYTES / 4;  // [2][256]
-  uint64_t* bars = (uint64_t*)(sbias + 512);
+  float* sbias = staging + GEMM_STAGING_BYTES / 4;  // [2 accumulator buffers][GEMM_COLVEC_PLANES][256]
+  uint64_t* bars = (uint64_t*)(sbias + 2 * GEMM_COLVEC_PLANES * 256);
   uint64_t* full_bar = bars;                          // [n_stages]
   uint64_t* empty_bar = bars + GEMM_MAX_STAGES;       // [n_stages]
   uint64_t* tmem_full = bars + 2 * GEMM_MAX_STAGES;   // [2]
@@ -428,9 +527,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       const int m0 = unit_m0(tile);
       const int tn = tile % tiles_n;
       const int n0 = tn * BN;
-      float* sb = sbias + ab * 256;
-      // bias tile -> smem (visible to the 4 epilogue warps after the named barrier)
-      for (int c = et; c < BN; c += 32 * GEMM_EPI_WARPS) sb[c] = (p.bias != nullptr && n0 + c < p.N) ? __ldg(p.bias + n0 + c) : 0.f;
+      float* sb = sbias + ab * (GEMM_COLVEC_PLANES * 256);
+      // per-column vectors of this tile -> smem (visible to the epilogue warps after the named barrier)
+      for (int c = et; c < BN; c += 32 * GEMM_EPI_WARPS) {
+        sb[c] = (p.bias != nullptr && n0 + c < p.N) ? __ldg(p.bias + n0 + c) : 0.f;
+        if (E::GENERIC ? (p.row_stats != nullptr) : E::LNA) sb[256 + c] = (n0 + c < p.N) ? __ldg(p.ln_c1 + n0 + c) : 0.f;
+        if (E::GENERIC ? (p.res_stats != nullptr) : E::LNR) {
+          const int oc = tn * bn_out + c;  // output column (no GLU with a LayerNorm'd residual)
+          const bool okc = c < bn_out && oc < n_out;
+          sb[512 + c] = okc ? __ldg(p.res_gamma + oc) : 0.f;
+          sb[768 + c] = okc ? __ldg(p.res_beta + oc) : 0.f;
+        }
+      }
       named_bar_sync(1, 32 * GEMM_EPI_WARPS);
       mbar_wait(&tmem_full[ab], aphase);
       tcgen05_fence_after();
@@ -457,7 +565,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 
 inline size_t gemm_smem_bytes(int block_n, int split, int n_stages, int two_cta = 0) {
   const size_t stage = (size_t)(GEMM_A_TILE_BYTES + (two_cta ? block_n / 2 : block_n) * 128) * (split ? 2 : 1);
-  return 1024 /*align slack*/ + n_stages * stage + GEMM_STAGING_BYTES + 512 * 4 + (2 * GEMM_MAX_STAGES + 4) * 8 + 16;
+  return 1024 /*align slack*/ + n_stages * stage + GEMM_STAGING_BYTES + 2 * GEMM_COLVEC_PLANES * 256 * 4 + (2 * GEMM_MAX_STAGES + 4) * 8 + 16;
 }
 
 }  // namespace vima

@@ -15,8 +15,11 @@ struct NormParams {
   unsigned short* out_hi; unsigned short* out_lo; int ld_o16;  // last norm's output as 16-bit operands, optional
   int dtype;
   unsigned char* out_lo8; unsigned char* out_hi8; int ld_o8;   // e4m3 cross-term views, optional
+  float* stats_out; float stats_eps;  // optional [rows, 2] = (mean, rstd) of the FIRST norm's output rows (for a LayerNorm folded downstream)
 };
 cudaError_t launch_norm(const NormParams& p, cudaStream_t stream);
+cudaError_t launch_row_stats_finalize(const float* partial, long long rows, int parts, int cols, float eps, int rms, float* stats,
+                                      cudaStream_t stream);
 
 struct AttnParams {
   const unsigned short *q_hi, *q_lo; int ldq;  // [B*Lq, ldq]; pointer already at head 0's first column
@@ -35,8 +38,8 @@ struct AttnParams {
 cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream);
 size_t attention_smem_bytes(const AttnParams& p);             // dynamic shared memory the mma.sync kernel needs for p
 int attention_max_lk(const AttnParams& p, size_t smem_limit);  // largest Lk (multiple of 64) that fits smem_limit at p's format
-bool attention_tc_supported(const AttnParams& p);  // tcgen05 variant (attention_tc.cu): head_dim 32, split operands, no bias
-cudaError_t launch_attention_tc(const AttnParams& p, cudaStream_t stream);
+bool attention_tc_supported(const AttnParams& p);  // tcgen05 variant (attention_tc.cu): head_dim 32, split operands, no bias, Lk <= 512
+cudaError_t launch_attention_tc(const AttnParams& p, void* encode_tiled_fn, cudaStream_t stream);  // encode_tiled_fn: cuTensorMapEncodeTiled
 
 struct SmallAttnParams {  // tiny-sequence fp32 attention (ViT: 5 tokens, 24 heads of 32)
   const float* qkv; int ld;        // [N*S, ld], q | k | v each W wide

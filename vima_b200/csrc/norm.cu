@@ -72,6 +72,20 @@ __global__ void __launch_bounds__(256) norm_rows_kernel(const NormParams p) {
   };
 
   if (p.w) sum = normalise(p.w, p.b, p.eps, p.rms != 0, sum);
+  if (p.stats_out) {  // statistics of the rows just produced: the consumer GEMM applies the next LayerNorm in its epilogue
+    const float mean = p.rms ? 0.f : warp_sum(sum) * inv_n;  // rms: statistics for a folded T5 RMSNorm (no centring)
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NORM_MAX_V4; ++i) {
+      const int c = i * 32 + lane;
+      if (c < nv4) {
+        const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+        sq += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) * inv_n + p.stats_eps);
+    if (lane == 0) reinterpret_cast<float2*>(p.stats_out)[row] = make_float2(mean, rstd);
+  }
   if (p.out_f32) {
     float4* o4 = reinterpret_cast<float4*>(p.out_f32 + row * p.ld_o32);
 #pragma unroll
@@ -120,6 +134,33 @@ __global__ void __launch_bounds__(256) norm_rows_kernel(const NormParams p) {
       }
     }
   }
+}
+
+// partial [rows, parts, 2] = (sum, sum of squares) over disjoint column sets -> stats [rows, 2] = (mean, rstd).  Combined in fp64 in
+// a fixed order (the partials themselves are fp32 sums of <= 128 values each, written by the GEMM epilogues).
+__global__ void __launch_bounds__(256) row_stats_finalize_kernel(const float2* __restrict__ partial, long long rows, int parts, double inv_n, float eps,
+                                                                 int rms, float2* __restrict__ stats) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int i = 0; i < parts; ++i) {
+    const float2 v = __ldg(partial + r * parts + i);
+    s1 += (double)v.x;
+    s2 += (double)v.y;
+  }
+  const double mean = rms ? 0.0 : s1 * inv_n;  // rms: T5 RMSNorm statistics (mean 0, rstd = 1/sqrt(mean(x^2) + eps))
+  double var = s2 * inv_n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  stats[r] = make_float2((float)mean, rsqrtf((float)var + eps));
+}
+
+cudaError_t launch_row_stats_finalize(const float* partial, long long rows, int parts, int cols, float eps, int rms, float* stats,
+                                      cudaStream_t stream) {
+  if (rows == 0) return cudaSuccess;
+  const unsigned blocks = (unsigned)((rows + 255) / 256);
+  row_stats_finalize_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float2*>(partial), rows, parts, 1.0 / (double)cols, eps, rms,
+                                                        reinterpret_cast<float2*>(stats));
+  return cudaGetLastError();
 }
 
 cudaError_t launch_norm(const NormParams& p, cudaStream_t stream) {

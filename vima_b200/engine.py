@@ -101,7 +101,7 @@ class Opnd:
 class PackedWeight:
     """K-major 16-bit packed weight [n_rows, ld] (+lo), optional fp32 bias in accumulator-column order."""
 
-    __slots__ = ("hi", "lo", "n", "k", "ld", "inv_scale", "bias", "glu", "block_n", "n_out", "hi8", "lo8")
+    __slots__ = ("hi", "lo", "n", "k", "ld", "inv_scale", "bias", "glu", "block_n", "n_out", "hi8", "lo8", "ln_c1", "ln_cols")
 
 
 def _pow2_scale(w_absmax: float, p: Prec) -> float:
@@ -111,11 +111,37 @@ def _pow2_scale(w_absmax: float, p: Prec) -> float:
     return 2.0 ** math.floor(math.log2(1024.0 / w_absmax))
 
 
-def pack_linear(ctx: _C.Context, weight: torch.Tensor, bias: Optional[torch.Tensor], *, transposed: bool, p: Prec, f8: bool = False) -> PackedWeight:
-    """nn.Linear weight [n, k] or HF Conv1D weight [k, n] (transposed=True).  f8: also the e4m3 cross-term views."""
+def fold_layernorm(w_nk: torch.Tensor, bias: Optional[torch.Tensor], gamma: torch.Tensor, beta: Optional[torch.Tensor], rows: Optional[torch.Tensor] = None):
+    """LayerNorm folded into the Linear that consumes it:  W (gamma*(x-mean)*rstd + beta) + b
+         = rstd * ((W*gamma) x - mean * c1) + c2,   c1 = rowsum(W*gamma),  c2 = b + W beta.
+    w_nk: [n, k] fp32.  `rows`: bool [n] selecting the output rows the fold applies to (None = all; the others stay as they are).
+    Returns (W', c1, c2) fp32, computed in fp64."""
+    w64 = w_nk.double()
+    g = gamma.detach().double()
+    wp = w64 * g[None, :]
+    c1 = wp.sum(dim=1)
+    c2 = torch.zeros(w_nk.shape[0], dtype=torch.float64, device=w_nk.device) if bias is None else bias.detach().double().clone()
+    add = torch.zeros_like(c2) if beta is None else w64 @ beta.detach().double()
+    if rows is not None:
+        wp = torch.where(rows[:, None], wp, w64)
+        c1 = torch.where(rows, c1, torch.zeros_like(c1))
+        add = torch.where(rows, add, torch.zeros_like(add))
+    return wp.float().contiguous(), c1.float().contiguous(), (c2 + add).float().contiguous()
+
+
+def pack_linear(ctx: _C.Context, weight: torch.Tensor, bias: Optional[torch.Tensor], *, transposed: bool, p: Prec, f8: bool = False,
+                ln: Optional[Tuple[torch.Tensor, Optional[torch.Tensor]]] = None) -> PackedWeight:
+    """nn.Linear weight [n, k] or HF Conv1D weight [k, n] (transposed=True).  f8: also the e4m3 cross-term views.
+    ln = (gamma, beta): the LayerNorm that feeds this layer is folded into the packed weight / bias (see `fold_layernorm`); the
+    GEMM then takes the UN-normalised rows plus their (mean, rstd)."""
     w = weight.detach()
     if w.dtype != torch.float32:
         w = w.float()
+    ln_c1 = None
+    if ln is not None:
+        w_nk = w.t() if transposed else w
+        w, ln_c1, bias = fold_layernorm(w_nk.contiguous(), bias, ln[0], ln[1])
+        transposed = False
     w = w.contiguous()
     n, k = (w.shape[1], w.shape[0]) if transposed else (w.shape[0], w.shape[1])
     pw = PackedWeight()
@@ -134,18 +160,27 @@ def pack_linear(ctx: _C.Context, weight: torch.Tensor, bias: Optional[torch.Tens
         ctx.pack_weight_f8(w, pw.hi8, pw.lo8, transposed=transposed, scale=scale)
     pw.bias = None if bias is None else bias.detach().float().contiguous()
     pw.glu, pw.block_n, pw.n_out = 0, 0, n
+    pw.ln_c1, pw.ln_cols = ln_c1, (1 if ln_c1 is not None else 0)
     return pw
 
 
 def pack_glu(ctx: _C.Context, w_val: torch.Tensor, b_val: Optional[torch.Tensor], w_gate: torch.Tensor, *, val_transposed: bool,
-             gate_transposed: bool, p: Prec, f8: bool = False) -> PackedWeight:
-    """Interleaves value / gate rows per accumulator tile so one GEMM + GLU epilogue yields act(x Wv + b) * (x Wg)."""
+             gate_transposed: bool, p: Prec, f8: bool = False, ln: Optional[Tuple[torch.Tensor, Optional[torch.Tensor]]] = None,
+             ln_gate: bool = True) -> PackedWeight:
+    """Interleaves value / gate rows per accumulator tile so one GEMM + GLU epilogue yields act(x Wv + b) * (x Wg).
+    ln = (gamma, beta): fold the LayerNorm in front of the value projection (and of the gate projection when `ln_gate`; the
+    XAttention gate reads the un-normalised stream, components.py:218-221) into the packed weights."""
     wv = w_val.detach().float()
     wg = w_gate.detach().float()
     wv = wv.t() if val_transposed else wv
     wg = wg.t() if gate_transposed else wg
     n_out, k = wv.shape
     assert wg.shape == (n_out, k)
+    c1v = c1g = bg = None
+    if ln is not None:
+        wv, c1v, b_val = fold_layernorm(wv.contiguous(), b_val, ln[0], ln[1])
+        if ln_gate:
+            wg, c1g, bg = fold_layernorm(wg.contiguous(), None, ln[0], ln[1])
     bn = ctx.glu_block_n(n_out)
     half = bn // 2
     tiles = (n_out + half - 1) // half
@@ -159,8 +194,16 @@ def pack_glu(ctx: _C.Context, w_val: torch.Tensor, b_val: Optional[torch.Tensor]
     W[:, 1] = wg_p
     if b_val is not None:
         Bv[:, 0] = torch.nn.functional.pad(b_val.detach().float(), (0, pad)).view(tiles, half)
+    if bg is not None:
+        Bv[:, 1] = torch.nn.functional.pad(bg, (0, pad)).view(tiles, half)
     pw = pack_linear(ctx, W.view(tiles * bn, k), Bv.view(tiles * bn), transposed=False, p=p, f8=f8)
     pw.glu, pw.block_n, pw.n_out = 1, bn, n_out
+    if ln is not None:
+        C1 = torch.zeros((tiles, 2, half), dtype=torch.float32, device=dev)
+        C1[:, 0] = torch.nn.functional.pad(c1v, (0, pad)).view(tiles, half)
+        if c1g is not None:
+            C1[:, 1] = torch.nn.functional.pad(c1g, (0, pad)).view(tiles, half)
+        pw.ln_c1, pw.ln_cols = C1.view(tiles * bn).contiguous(), (1 if ln_gate else 2)
     return pw
 
 
@@ -190,9 +233,12 @@ class WeightCache:
 # -------------------------------------------------------------------------------------------------------------
 def gemm(ctx: _C.Context, a: Opnd, w: PackedWeight, p: Prec, *, act=_C.ACT_NONE, residual=None, mul=None, out_f32: Optional[torch.Tensor] = None,
          out16: Optional[Opnd] = None, want_f32=False, want16=False, out16_ld: Optional[int] = None, rows: Optional[int] = None,
-         out_f8: bool = False):
+         out_f8: bool = False, row_stats: Optional[torch.Tensor] = None, res_ln=None, stats_out: Optional[torch.Tensor] = None):
     """out = epilogue(a @ w^T).  Returns (out_f32 | None, out16 | None).  out_f8: the 16-bit output carries e4m3 cross-term views
-    (it feeds an "f16f8" GEMM) instead of a 16-bit lo part (attention inputs keep the 16-bit pair)."""
+    (it feeds an "f16f8" GEMM) instead of a 16-bit lo part (attention inputs keep the 16-bit pair).
+    row_stats: fp32 [M, 2] (mean, rstd) of the rows of `a` for a weight packed with a folded LayerNorm (`pack_*(ln=...)`).
+    res_ln = (stats [M,2], gamma, beta): the residual rows are LayerNorm'd on the fly.  stats_out: fp32 [M, parts, 2] receiving the
+    per-row partial (sum, sum of squares) of the output (`stats_buffer`, `row_stats_of`)."""
     M = a.rows if rows is None else rows
     if a.cols != w.k:
         raise ValueError(f"gemm: operand has {a.cols} columns, weight expects {w.k}")
@@ -201,6 +247,8 @@ def gemm(ctx: _C.Context, a: Opnd, w: PackedWeight, p: Prec, *, act=_C.ACT_NONE,
         out_f32 = torch.empty((M, w.n_out), dtype=torch.float32, device=dev)
     if want16 and out16 is None:
         out16 = Opnd(M, w.n_out, dev, p.split, ld=out16_ld, f8=out_f8 and p.f8)
+    if (row_stats is None) != (w.ln_c1 is None):
+        raise RuntimeError("gemm: a weight packed with a folded LayerNorm needs the operand's row statistics (and only such a weight takes them)")
     if M == 0:
         return out_f32, out16
     use_f8 = a.lo8 is not None and w.lo8 is not None
@@ -211,8 +259,25 @@ def gemm(ctx: _C.Context, a: Opnd, w: PackedWeight, p: Prec, *, act=_C.ACT_NONE,
              out_hi=None if out16 is None else out16.hi, out_lo=None if out16 is None else out16.lo,
              ld_o16=0 if out16 is None else out16.ld, block_n=w.block_n,
              a_lo8=a.lo8 if use_f8 else None, a_hi8=a.hi8 if use_f8 else None, b_hi8=w.hi8 if use_f8 else None, b_lo8=w.lo8 if use_f8 else None,
-             out_lo8=None if out16 is None else out16.lo8, out_hi8=None if out16 is None else out16.hi8)
+             out_lo8=None if out16 is None else out16.lo8, out_hi8=None if out16 is None else out16.hi8,
+             row_stats=row_stats, ln_c1=w.ln_c1, ln_cols=w.ln_cols if row_stats is not None else 0,
+             res_stats=None if res_ln is None else res_ln[0], res_gamma=None if res_ln is None else res_ln[1],
+             res_beta=None if res_ln is None else res_ln[2], stats_out=stats_out)
     return out_f32, out16
+
+
+def stats_buffer(ctx: _C.Context, M: int, w: PackedWeight, device) -> torch.Tensor:
+    """fp32 [M, parts, 2] for the partial row statistics a GEMM with weight `w` emits."""
+    return torch.empty((max(M, 1), ctx.gemm_stats_parts(w.n, w.glu, w.block_n), 2), dtype=torch.float32, device=device)
+
+
+def row_stats_of(ctx: _C.Context, partial: torch.Tensor, rows: int, cols: int, eps: float, rms: bool = False) -> torch.Tensor:
+    """partial statistics [rows, parts, 2] -> (mean, rstd) [rows, 2] of a `cols`-wide row (biased variance, nn.LayerNorm; rms: the
+    T5 RMSNorm form (0, 1/sqrt(mean(x^2) + eps)))."""
+    out = torch.empty((max(rows, 1), 2), dtype=torch.float32, device=partial.device)
+    if rows:
+        ctx.row_stats_finalize(partial[:rows], cols, eps, out, rms=rms)
+    return out
 
 
 def to_operand(ctx: _C.Context, x: torch.Tensor, p: Prec, *, pad_cols: Optional[int] = None) -> Opnd:
@@ -230,16 +295,22 @@ def to_operand(ctx: _C.Context, x: torch.Tensor, p: Prec, *, pad_cols: Optional[
 
 
 def norm(ctx: _C.Context, x: torch.Tensor, p: Prec, *, rows: int, cols: int, ldx: Optional[int] = None, w=None, b=None, eps=1e-5, rms=False,
-         add=None, w2=None, b2=None, eps2=1e-5, want_f32=False, want2_f32=False, want16=False, out_f32=None, out_f8: bool = False):
+         add=None, w2=None, b2=None, eps2=1e-5, want_f32=False, want2_f32=False, want16=False, out_f32=None, out_f8: bool = False,
+         stats_eps: Optional[float] = None):
+    """Returns (y1 fp32 | None, y2 fp32 | None, operands of the last norm | None[, (mean, rstd) [rows, 2] of y1 when stats_eps is given])."""
     dev = x.device
     ldx = cols if ldx is None else ldx
     o32 = out_f32 if out_f32 is not None else (torch.empty((rows, cols), dtype=torch.float32, device=dev) if want_f32 else None)
     o2 = torch.empty((rows, cols), dtype=torch.float32, device=dev) if want2_f32 else None
     o16 = Opnd(rows, cols, dev, p.split, f8=out_f8 and p.f8) if want16 else None
+    st = torch.empty((max(rows, 1), 2), dtype=torch.float32, device=dev) if stats_eps is not None else None
     if rows:
         ctx.norm(x, rows=rows, cols=cols, ldx=ldx, w=w, b=b, eps=eps, rms=int(rms), add=add, w2=w2, b2=b2, eps2=eps2, out_f32=o32,
                  out2_f32=o2, out_hi=None if o16 is None else o16.hi, out_lo=None if o16 is None else o16.lo, dtype=p.dtype,
-                 out_lo8=None if o16 is None else o16.lo8, out_hi8=None if o16 is None else o16.hi8)
+                 out_lo8=None if o16 is None else o16.lo8, out_hi8=None if o16 is None else o16.hi8, stats_out=st,
+                 stats_eps=1e-5 if stats_eps is None else stats_eps)
+    if stats_eps is not None:
+        return o32, o2, o16, st
     return o32, o2, o16
 
 

@@ -45,29 +45,37 @@ class ResidualAttentionBlock(nn.Module):
 
 
 def pack_vit_blocks(ctx, blocks, p):
+    """ln_1 / ln_2 are folded into in_proj / c_fc (engine.fold_layernorm): those GEMMs read the un-normalised residual stream."""
     return [{
-        "in": eng.pack_linear(ctx, blk.attn.in_proj_weight, blk.attn.in_proj_bias, transposed=False, p=p),
+        "in": eng.pack_linear(ctx, blk.attn.in_proj_weight, blk.attn.in_proj_bias, transposed=False, p=p, f8=True,
+                              ln=(blk.ln_1.weight.detach(), blk.ln_1.bias.detach())),
         "out": eng.pack_linear(ctx, blk.attn.out_proj.weight, blk.attn.out_proj.bias, transposed=False, p=p),
-        "fc": eng.pack_linear(ctx, blk.mlp.c_fc.weight, blk.mlp.c_fc.bias, transposed=False, p=p),
-        "pr": eng.pack_linear(ctx, blk.mlp.c_proj.weight, blk.mlp.c_proj.bias, transposed=False, p=p),
+        "fc": eng.pack_linear(ctx, blk.mlp.c_fc.weight, blk.mlp.c_fc.bias, transposed=False, p=p, f8=True,
+                              ln=(blk.ln_2.weight.detach(), blk.ln_2.bias.detach())),
+        "pr": eng.pack_linear(ctx, blk.mlp.c_proj.weight, blk.mlp.c_proj.bias, transposed=False, p=p, f8=True),
     } for blk in blocks]
 
 
-def run_vit_blocks(ctx, p, blocks, Wblocks, x32, y16, N, S, Wm, heads):
-    """Pre-LN residual blocks (vit.py:199-236). x32: residual stream [N*S, W] (updated in place by the GEMM epilogues),
-    y16: ln_1(x) of the first block as operands.  Returns the final residual stream."""
+def run_vit_blocks(ctx, p, blocks, Wblocks, x32, x16, st, N, S, Wm, heads):
+    """Pre-LN residual blocks (vit.py:199-236). x32: residual stream [N*S, W] (updated in place by the GEMM epilogues), x16: the
+    same rows as GEMM operands, st: their (mean, rstd) for the first block's ln_1.  No LayerNorm kernel runs inside the blocks: the
+    residual-carrying GEMMs (out_proj, c_proj) emit operands + row sums, in_proj / c_fc apply ln_1 / ln_2 in their epilogues.
+    Returns the final residual stream."""
     dev = x32.device
-    att16 = eng.Opnd(N * S, Wm, dev, p.split)
+    M = N * S
+    att16 = eng.Opnd(M, Wm, dev, p.split)
     for i, (blk, Wb) in enumerate(zip(blocks, Wblocks)):
-        qkv32, _ = eng.gemm(ctx, y16, Wb["in"], p, want_f32=True)
+        qkv32, _ = eng.gemm(ctx, x16, Wb["in"], p, want_f32=True, row_stats=st)
         ctx.small_attention(qkv32, N=N, S=S, H=heads, W=Wm, scale=1.0 / math.sqrt(Wm // heads), o_hi=att16.hi, o_lo=att16.lo, dtype=p.dtype)
-        eng.gemm(ctx, att16, Wb["out"], p, residual=x32, out_f32=x32)
-        _, _, y16 = eng.norm(ctx, x32, p, rows=N * S, cols=Wm, w=blk.ln_2.weight.detach(), b=blk.ln_2.bias.detach(), eps=blk.ln_2.eps, want16=True)
-        _, h16 = eng.gemm(ctx, y16, Wb["fc"], p, act=_C.ACT_QUICKGELU, want16=True)
-        eng.gemm(ctx, h16, Wb["pr"], p, residual=x32, out_f32=x32)
-        if i + 1 < len(blocks):
-            nb = blocks[i + 1]
-            _, _, y16 = eng.norm(ctx, x32, p, rows=N * S, cols=Wm, w=nb.ln_1.weight.detach(), b=nb.ln_1.bias.detach(), eps=nb.ln_1.eps, want16=True)
+        part = eng.stats_buffer(ctx, M, Wb["out"], dev)
+        _, x16 = eng.gemm(ctx, att16, Wb["out"], p, residual=x32, out_f32=x32, want16=True, out_f8=True, stats_out=part)
+        st2 = eng.row_stats_of(ctx, part, M, Wm, blk.ln_2.eps)
+        _, h16 = eng.gemm(ctx, x16, Wb["fc"], p, act=_C.ACT_QUICKGELU, want16=True, out_f8=True, row_stats=st2)
+        last = i + 1 == len(blocks)
+        part = None if last else eng.stats_buffer(ctx, M, Wb["pr"], dev)
+        _, x16 = eng.gemm(ctx, h16, Wb["pr"], p, residual=x32, out_f32=x32, want16=not last, out_f8=True, stats_out=part)
+        if not last:
+            st = eng.row_stats_of(ctx, part, M, Wm, blocks[i + 1].ln_1.eps)
     return x32
 
 
@@ -115,9 +123,9 @@ class VisionTransformer(nn.Module):
         tok32 = torch.empty((N * S, Wm), dtype=torch.float32, device=dev)
         ctx.vit_tokens(pe32, self.cls_token.detach(), self.pos_embed.detach(), N, S, Wm, tok32)
         b0 = self.blocks[0]
-        x32, _, y16 = eng.norm(ctx, tok32, p, rows=N * S, cols=Wm, w=self.ln_pre.weight.detach(), b=self.ln_pre.bias.detach(), eps=self.ln_pre.eps,
-                               w2=b0.ln_1.weight.detach(), b2=b0.ln_1.bias.detach(), eps2=b0.ln_1.eps, want_f32=True, want16=True)
-        x32 = run_vit_blocks(ctx, p, self.blocks, W["blocks"], x32, y16, N, S, Wm, self.heads)
+        x32, _, x16, st = eng.norm(ctx, tok32, p, rows=N * S, cols=Wm, w=self.ln_pre.weight.detach(), b=self.ln_pre.bias.detach(), eps=self.ln_pre.eps,
+                                   want_f32=True, want16=True, out_f8=True, stats_eps=b0.ln_1.eps)
+        x32 = run_vit_blocks(ctx, p, self.blocks, W["blocks"], x32, x16, st, N, S, Wm, self.heads)
         # ln_post on the CLS rows (row stride S*width), then @ projection
         _, _, cls16 = eng.norm(ctx, x32, p, rows=N, cols=Wm, ldx=S * Wm, w=self.ln_post.weight.detach(), b=self.ln_post.bias.detach(),
                                eps=self.ln_post.eps, want16=True)
@@ -314,9 +322,9 @@ class GatoVisionTransformerRectangular(nn.Module):
         tok32 = torch.empty((N * S, Wm), dtype=torch.float32, device=dev)
         ctx.vit_tokens(pe32, None, self.pos_embed.detach(), N, S, Wm, tok32)
         b0 = self.blocks[0]
-        x32, _, y16 = eng.norm(ctx, tok32, p, rows=N * S, cols=Wm, w=self.ln_pre.weight.detach(), b=self.ln_pre.bias.detach(), eps=self.ln_pre.eps,
-                               w2=b0.ln_1.weight.detach(), b2=b0.ln_1.bias.detach(), eps2=b0.ln_1.eps, want_f32=True, want16=True)
-        x32 = run_vit_blocks(ctx, p, self.blocks, W["blocks"], x32, y16, N, S, Wm, self.heads)
+        x32, _, x16, st = eng.norm(ctx, tok32, p, rows=N * S, cols=Wm, w=self.ln_pre.weight.detach(), b=self.ln_pre.bias.detach(), eps=self.ln_pre.eps,
+                                   want_f32=True, want16=True, out_f8=True, stats_eps=b0.ln_1.eps)
+        x32 = run_vit_blocks(ctx, p, self.blocks, W["blocks"], x32, x16, st, N, S, Wm, self.heads)
         _, _, post16 = eng.norm(ctx, x32, p, rows=N * S, cols=Wm, w=self.ln_post.weight.detach(), b=self.ln_post.bias.detach(), eps=self.ln_post.eps,
                                 want16=True)
         out32, _ = eng.gemm(ctx, post16, W["proj"], p, want_f32=True)

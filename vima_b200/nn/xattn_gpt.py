@@ -6,10 +6,13 @@ residual epilogues, fused masked attention, warp-shuffle LayerNorm).  Per layer 
 
     XAttention (pre-LN, bias-free, components.py:158-228)        Block (GPT-1 post-LN, components.py:23-37)
       q  = Wq LN(x)            k,v = Wkv (prompt + pos)             qkv = c_attn(x)
-      a  = Wo attn(q,k,v) + x                                       s   = c_proj(causal_attn(qkv)) + x
-      g  = Wg a                (gate reads UN-normalised a)         n   = LN1(s)
-      h  = gelu(W1 LN2(a)) * g                                      h   = gelu(c_fc n) * (Wg n)     [one GEMM, GLU epilogue]
-      x' = W2 h + a                                                 x'' = LN2(c_proj h + n)
+      a  = Wo attn(q,k,v) + x          [+ row sums of a]            s   = c_proj(causal_attn(qkv)) + x   [+ row sums of s]
+      h  = gelu(W1 LN2(a)) * (Wg a)    [ONE GEGLU GEMM over a:      h   = gelu(c_fc LN1(s)) * (Wg LN1(s))  [one GEGLU GEMM over s,
+           LN2 folded into W1, the gate reads UN-normalised a]            LN1 folded into both halves]
+      x' = W2 h + a                                                 x'' = LN2(c_proj h + LN1(s))   [LN1(s) rebuilt in the epilogue]
+
+LayerNorm folding: W (gamma (x - mean) rstd + beta) = rstd ((W gamma) x - mean rowsum(W gamma)) + W beta, so the GEMM
+runs on the un-normalised rows and its epilogue applies (mean, rstd); the producing GEMM's epilogue emits the row sums.
 """
 from __future__ import annotations
 
@@ -53,11 +56,13 @@ class Block(nn.Module):
 
 
 def pack_block(ctx, blk: "Block", p) -> dict:
+    """Packed weights of one GPT block.  ln_1 is folded into c_fc || gated_layer (both read ln_1(s), components.py:31-36)."""
+    ln1 = (blk.ln_1.weight.detach(), blk.ln_1.bias.detach())
     return {
         "c_attn": eng.pack_linear(ctx, blk.attn.c_attn.weight, blk.attn.c_attn.bias, transposed=True, p=p, f8=True),
         "c_proj": eng.pack_linear(ctx, blk.attn.c_proj.weight, blk.attn.c_proj.bias, transposed=True, p=p, f8=True),
         "fc_glu": eng.pack_glu(ctx, blk.mlp.c_fc.weight, blk.mlp.c_fc.bias, blk.mlp.gated_layer.weight, val_transposed=True,
-                               gate_transposed=False, p=p, f8=True),
+                               gate_transposed=False, p=p, f8=True, ln=ln1, ln_gate=True),
         "mlp_proj": eng.pack_linear(ctx, blk.mlp.c_proj.weight, blk.mlp.c_proj.bias, transposed=True, p=p, f8=True),
     }
 
@@ -101,9 +106,14 @@ def run_block(ctx, p, W, blk: "Block", x32, x16, c16, *, B, L, E, H, omask, chai
               layer=0):
     """GPT-1 post-LN block (components.py:23-37 / gpt.py:223-249): returns (LN2 output fp32, operands of the NEXT consumer):
     with `chain_ln` the operands are chain_ln(LN2(...)) (next layer's query LayerNorm), with `want16` they are LN2(...) itself.
-    With `cache` the L rows are the NEW tokens of each episode and attention runs over the cached prefix + themselves."""
+    With `cache` the L rows are the NEW tokens of each episode and attention runs over the cached prefix + themselves.
+
+    ln_1 never runs as a kernel: c_proj's epilogue emits s = attn + x as fp32 + operands together with per-row partial sums, the
+    GEGLU GEMM takes the un-normalised s with ln_1 folded into its weights (rstd / mean applied in its epilogue), and the MLP's
+    c_proj normalises its residual ln_1(s) on the fly from the same (mean, rstd)."""
     M = B * L
     d = E // H
+    dev = x32.device
     # operand formats: attention inputs keep the 16-bit (hi, lo) pair; everything that only feeds a GEMM carries e4m3
     # cross-term views in "f16f8" mode (out_f8=True is a no-op in the other modes)
     _, qkv16 = eng.gemm(ctx, x16, W["c_attn"], p, want16=True)
@@ -119,18 +129,18 @@ def run_block(ctx, p, W, blk: "Block", x32, x16, c16, *, B, L, E, H, omask, chai
         ctx.attention(q=(qkv16.hi, qkv16.lo, qkv16.ld, 0), k=(khi, klo, 2 * E, 0), v=(khi, klo, 2 * E, E), o=(c16.hi, c16.lo, c16.ld, 0),
                       B=B, H=H, Lq=L, Lk=L0 + L, D=d, scale=1.0 / math.sqrt(d), causal=True, key_mask=cache.mask, dtype=p.dtype, o8=o8,
                       kv_batch_rows=cache.Lmax, mask_ld=cache.Lmax, q_pos0=L0)
-    s32, _ = eng.gemm(ctx, c16, W["c_proj"], p, residual=x32, want_f32=True)
-    n32, _, n16 = eng.norm(ctx, s32, p, rows=M, cols=E, w=blk.ln_1.weight.detach(), b=blk.ln_1.bias.detach(), eps=blk.ln_1.eps, want_f32=True,
-                           want16=True, out_f8=True)
-    _, h16 = eng.gemm(ctx, n16, W["fc_glu"], p, act=_C.ACT_GELU, want16=True, out_f8=True)
-    s32, _ = eng.gemm(ctx, h16, W["mlp_proj"], p, residual=n32, out_f32=s32)
-    del h16
+    part = eng.stats_buffer(ctx, M, W["c_proj"], dev)
+    s32, s16 = eng.gemm(ctx, c16, W["c_proj"], p, residual=x32, want_f32=True, want16=True, out_f8=True, stats_out=part)
+    st = eng.row_stats_of(ctx, part, M, E, blk.ln_1.eps)
+    _, h16 = eng.gemm(ctx, s16, W["fc_glu"], p, act=_C.ACT_GELU, want16=True, out_f8=True, row_stats=st)
+    t32, _ = eng.gemm(ctx, h16, W["mlp_proj"], p, residual=s32, res_ln=(st, blk.ln_1.weight.detach(), blk.ln_1.bias.detach()), want_f32=True)
+    del h16, s32, s16
     w, b = blk.ln_2.weight.detach(), blk.ln_2.bias.detach()
     if chain_ln is not None:
-        y32, _, nxt16 = eng.norm(ctx, s32, p, rows=M, cols=E, w=w, b=b, eps=blk.ln_2.eps, w2=chain_ln.weight.detach(), b2=chain_ln.bias.detach(),
+        y32, _, nxt16 = eng.norm(ctx, t32, p, rows=M, cols=E, w=w, b=b, eps=blk.ln_2.eps, w2=chain_ln.weight.detach(), b2=chain_ln.bias.detach(),
                                  eps2=chain_ln.eps, want16=True, out_f32=out_f32, want_f32=out_f32 is None, out_f8=True)
     else:
-        y32, _, nxt16 = eng.norm(ctx, s32, p, rows=M, cols=E, w=w, b=b, eps=blk.ln_2.eps, want16=want16, out_f32=out_f32, want_f32=out_f32 is None,
+        y32, _, nxt16 = eng.norm(ctx, t32, p, rows=M, cols=E, w=w, b=b, eps=blk.ln_2.eps, want16=want16, out_f32=out_f32, want_f32=out_f32 is None,
                                  out_f8=True)
     return y32, nxt16
 
@@ -156,7 +166,7 @@ class PosIdGuard:
 
     def poll(self):
         """Raise if a PREVIOUS call saw a bad id (its flag copy has landed)."""
-        if self.event is not None and self.event.query():
+        if self.event is not None and not torch.cuda.is_current_stream_capturing() and self.event.query():
             self.event = None
             if int(self.host[0]) != 0:
                 self.reset()
@@ -255,8 +265,10 @@ class XAttnGPT(nn.Module):
                 d["wq"] = eng.pack_linear(ctx, xa.query.weight, None, transposed=False, p=p, f8=True)
                 d["wkv"] = eng.pack_linear(ctx, xa.key_value.weight, None, transposed=False, p=p, f8=True)
                 d["wo"] = eng.pack_linear(ctx, xa.attention_out.weight, None, transposed=False, p=p, f8=True)
-                d["w1"] = eng.pack_linear(ctx, xa.linear1.weight, None, transposed=False, p=p, f8=True)
-                d["wg"] = eng.pack_linear(ctx, xa.gated_layer.weight, None, transposed=False, p=p, f8=True)
+                # linear1 reads ln(a), the gate reads a itself (components.py:218-221): one GEGLU GEMM over the un-normalised a with
+                # `ln` folded into the value half only
+                d["w1g"] = eng.pack_glu(ctx, xa.linear1.weight, None, xa.gated_layer.weight, val_transposed=False, gate_transposed=False,
+                                        p=p, f8=True, ln=(xa.ln.weight.detach(), xa.ln.bias.detach()), ln_gate=False)
                 d["w2"] = eng.pack_linear(ctx, xa.linear2.weight, None, transposed=False, p=p, f8=True)
                 d.update(pack_block(ctx, blk, p))
                 L.append(d)
@@ -376,12 +388,10 @@ class XAttnGPT(nn.Module):
             ctx.attention(q=(q16.hi, q16.lo, q16.ld, 0), k=(kvp16.hi, kvp16.lo, kvp16.ld, 0), v=(kvp16.hi, kvp16.lo, kvp16.ld, E),
                           o=(c16.hi, c16.lo, c16.ld, 0), B=B, H=Hx, Lq=L, Lk=Lp, D=d_x, scale=1.0 / math.sqrt(d_x), causal=False,
                           key_mask=pmask, dtype=p.dtype, o8=None if c16.lo8 is None else (c16.lo8, c16.hi8))
-            a32, a16 = eng.gemm(ctx, c16, W["wo"], p, residual=x32, want_f32=True, want16=True, out_f8=True)
-            w, b = lnw(xa.ln)
-            _, _, n16 = eng.norm(ctx, a32, p, rows=M, cols=E, w=w, b=b, eps=xa.ln.eps, want16=True, out_f8=True)
-            g32, _ = eng.gemm(ctx, a16, W["wg"], p, want_f32=True)
-            _, h16 = eng.gemm(ctx, n16, W["w1"], p, act=_C.ACT_GELU, mul=g32, want16=True, out_f8=True)
-            del g32
+            part = eng.stats_buffer(ctx, M, W["wo"], dev)
+            a32, a16 = eng.gemm(ctx, c16, W["wo"], p, residual=x32, want_f32=True, want16=True, out_f8=True, stats_out=part)
+            st = eng.row_stats_of(ctx, part, M, E, xa.ln.eps)
+            _, h16 = eng.gemm(ctx, a16, W["w1g"], p, act=_C.ACT_GELU, want16=True, out_f8=True, row_stats=st)
             xb32, xb16 = eng.gemm(ctx, h16, W["w2"], p, residual=a32, want_f32=True, want16=True, out_f8=True)
             del h16, a32, a16
             # ---------------- causal Block ----------------
