@@ -121,11 +121,15 @@ class T5PromptEncoder(nn.Module):
             out = []
             for blk in self.t5.encoder.block:
                 sa, ff = blk.layer[0].SelfAttention, blk.layer[1].DenseReluDense
+                # "f16f8" operands throughout (2 tensor pass-equivalents).  The RMSNorms stay kernels here, unlike the decoder's /
+                # ViT's folded LayerNorms: T5's pre-norm residual stream is unbounded (t5-base hidden states reach 1e3-1e4 with
+                # real weights), and an un-normalised GEMM operand must stay below 1024 for the e4m3 cross terms (65504 for fp16)
                 out.append({
-                    "qkv": eng.pack_linear(ctx, torch.cat([sa.q.weight.detach(), sa.k.weight.detach(), sa.v.weight.detach()], 0), None, transposed=False, p=p),
-                    "o": eng.pack_linear(ctx, sa.o.weight, None, transposed=False, p=p),
-                    "wi": eng.pack_linear(ctx, ff.wi.weight, None, transposed=False, p=p),
-                    "wo": eng.pack_linear(ctx, ff.wo.weight, None, transposed=False, p=p),
+                    "qkv": eng.pack_linear(ctx, torch.cat([sa.q.weight.detach(), sa.k.weight.detach(), sa.v.weight.detach()], 0), None, transposed=False,
+                                           p=p, f8=True),
+                    "o": eng.pack_linear(ctx, sa.o.weight, None, transposed=False, p=p, f8=True),
+                    "wi": eng.pack_linear(ctx, ff.wi.weight, None, transposed=False, p=p, f8=True),
+                    "wo": eng.pack_linear(ctx, ff.wo.weight, None, transposed=False, p=p, f8=True),
                 })
             return out
 
@@ -158,21 +162,23 @@ class T5PromptEncoder(nn.Module):
             kmask = eng.as_u8(attention_mask.reshape(B, Lp) != 0)
         bias = self._bias_table(Lp, dev)
         eps = cfg["layer_norm_epsilon"]
-        _, _, n16 = eng.norm(ctx, h32, p, rows=Mp, cols=D, w=blocks[0].layer[0].layer_norm.weight.detach(), eps=eps, rms=True, want16=True)
-        c16 = eng.Opnd(Mp, inner, dev, p.split)
+        _, _, n16 = eng.norm(ctx, h32, p, rows=Mp, cols=D, w=blocks[0].layer[0].layer_norm.weight.detach(), eps=eps, rms=True, want16=True, out_f8=True)
+        c16 = eng.Opnd(Mp, inner, dev, p.split, f8=p.f8)
+        o8 = None if c16.lo8 is None else (c16.lo8, c16.hi8)
         out32 = out16 = None
         for i, (blk, Wb) in enumerate(zip(blocks, W)):
             _, qkv16 = eng.gemm(ctx, n16, Wb["qkv"], p, want16=True)
             ctx.attention(q=(qkv16.hi, qkv16.lo, qkv16.ld, 0), k=(qkv16.hi, qkv16.lo, qkv16.ld, inner), v=(qkv16.hi, qkv16.lo, qkv16.ld, 2 * inner),
                           o=(c16.hi, c16.lo, c16.ld, 0), B=B, H=H, Lq=Lp, Lk=Lp, D=dkv, scale=1.0, causal=False, key_mask=kmask, rel_bias=bias,
-                          dtype=p.dtype)
+                          dtype=p.dtype, o8=o8)
             eng.gemm(ctx, c16, Wb["o"], p, residual=h32, out_f32=h32)
-            _, _, n16 = eng.norm(ctx, h32, p, rows=Mp, cols=D, w=blk.layer[1].layer_norm.weight.detach(), eps=eps, rms=True, want16=True)
-            _, f16 = eng.gemm(ctx, n16, Wb["wi"], p, act=_C.ACT_RELU, want16=True)
+            _, _, n16 = eng.norm(ctx, h32, p, rows=Mp, cols=D, w=blk.layer[1].layer_norm.weight.detach(), eps=eps, rms=True, want16=True, out_f8=True)
+            _, f16 = eng.gemm(ctx, n16, Wb["wi"], p, act=_C.ACT_RELU, want16=True, out_f8=True)
             eng.gemm(ctx, f16, Wb["wo"], p, residual=h32, out_f32=h32)
             del f16
             if i + 1 < len(blocks):
-                _, _, n16 = eng.norm(ctx, h32, p, rows=Mp, cols=D, w=blocks[i + 1].layer[0].layer_norm.weight.detach(), eps=eps, rms=True, want16=True)
+                _, _, n16 = eng.norm(ctx, h32, p, rows=Mp, cols=D, w=blocks[i + 1].layer[0].layer_norm.weight.detach(), eps=eps, rms=True, want16=True,
+                                     out_f8=True)
             else:
                 out32, _, out16 = eng.norm(ctx, h32, p, rows=Mp, cols=D, w=self.t5.encoder.final_layer_norm.weight.detach(), eps=eps, rms=True,
                                            want_f32=True, want16=want16)
