@@ -183,42 +183,45 @@ __global__ void __launch_bounds__(ATC_THREADS, 3) attention_tc_kernel(const __gr
   const int kv_row0 = b * kvb;
 
   if (warp == 4) {
-    // =============================== control lane: TMA loads + MMA issue ===============================
-    if (lane == 0) {
-      uint32_t g = 0;                 // chunks issued so far (both passes): parity of s_* / p_* / v_full
-      uint32_t k_use[2] = {0u, 0u};   // completed fills of each K stage
-      auto load_k = [&](int c, int stage) {
-        uint8_t* dst = sm + OFF_K + stage * 8192;
-        mbar_arrive_expect_tx(&k_full[stage], 8192u);
-        tma_load_2d(dst, &P.tm_k_hi, &k_full[stage], x_col, kv_row0 + c * ATC_KC);
-        tma_load_2d(dst + 4096, &P.tm_k_lo, &k_full[stage], x_col, kv_row0 + c * ATC_KC);
-      };
-      auto load_v = [&](int c) {
-        mbar_arrive_expect_tx(v_full, 8192u);
-        tma_load_2d(sm + OFF_VH, &P.tm_v_hi, v_full, x_col, kv_row0 + c * ATC_KC);
-        tma_load_2d(sm + OFF_VL, &P.tm_v_lo, v_full, x_col, kv_row0 + c * ATC_KC);
-      };
-      auto issue_qk = [&](int c, uint32_t gg) {  // gg = global index of chunk c
-        const int stage = c & 1;
-        mbar_wait(&k_full[stage], k_use[stage] & 1u);
-        k_use[stage]++;
-        if (gg > 0) mbar_wait(s_free, (gg - 1) & 1u);  // S(previous chunk) has been read out
-        tcgen05_fence_after();
-        const uint64_t dqh = desc_sw64(sbase + OFF_QH), dql = desc_sw64(sbase + OFF_QL);
-        const uint64_t dkh = desc_sw64(sbase + OFF_K + stage * 8192), dkl = desc_sw64(sbase + OFF_K + stage * 8192 + 4096);
+    // =============================== control warp: lane 0 issues the TMA loads and the MMAs ===============================
+    // (the pass loop and its block-wide vote run at WARP level: an aligned barrier must be reached by the whole warp together)
+    uint32_t g = 0;                 // chunks issued so far (both passes): parity of s_* / p_* / v_full
+    uint32_t k_use[2] = {0u, 0u};   // completed fills of each K stage
+    int n = n_plan;
+    for (int pass = 0; pass < 2; ++pass) {
+      if (lane == 0) {
+        auto load_k = [&](int c, int stage) {
+          uint8_t* dst = sm + OFF_K + stage * 8192;
+          mbar_arrive_expect_tx(&k_full[stage], 8192u);
+          tma_load_2d(dst, &P.tm_k_hi, &k_full[stage], x_col, kv_row0 + c * ATC_KC);
+          tma_load_2d(dst + 4096, &P.tm_k_lo, &k_full[stage], x_col, kv_row0 + c * ATC_KC);
+        };
+        auto load_v = [&](int c) {
+          mbar_arrive_expect_tx(v_full, 8192u);
+          tma_load_2d(sm + OFF_VH, &P.tm_v_hi, v_full, x_col, kv_row0 + c * ATC_KC);
+          tma_load_2d(sm + OFF_VL, &P.tm_v_lo, v_full, x_col, kv_row0 + c * ATC_KC);
+        };
+        auto issue_qk = [&](int c, uint32_t gg) {  // gg = global index of chunk c
+          const int stage = c & 1;
+          mbar_wait(&k_full[stage], k_use[stage] & 1u);
+          k_use[stage]++;
+          if (gg > 0) mbar_wait(s_free, (gg - 1) & 1u);  // S(previous chunk) has been read out
+          tcgen05_fence_after();
+          const uint64_t dqh = desc_sw64(sbase + OFF_QH), dql = desc_sw64(sbase + OFF_QL);
+          const uint64_t dkh = desc_sw64(sbase + OFF_K + stage * 8192), dkl = desc_sw64(sbase + OFF_K + stage * 8192 + 4096);
 #pragma unroll
-        for (int k = 0; k < ATC_D / 16; ++k) umma_f16(tmem, dqh + 2 * k, dkh + 2 * k, idesc_s, (uint32_t)(k != 0));
+          for (int k = 0; k < ATC_D / 16; ++k) umma_f16(tmem, dqh + 2 * k, dkh + 2 * k, idesc_s, (uint32_t)(k != 0));
 #pragma unroll
-        for (int k = 0; k < ATC_D / 16; ++k) umma_f16(tmem, dql + 2 * k, dkh + 2 * k, idesc_s, 1u);
+          for (int k = 0; k < ATC_D / 16; ++k) umma_f16(tmem, dql + 2 * k, dkh + 2 * k, idesc_s, 1u);
 #pragma unroll
-        for (int k = 0; k < ATC_D / 16; ++k) umma_f16(tmem, dqh + 2 * k, dkl + 2 * k, idesc_s, 1u);
-        umma_commit(s_full);
-      };
-      mbar_arrive_expect_tx(q_full, 16384u);
-      tma_load_2d(sm + OFF_QH, &P.tm_q_hi, q_full, x_col, b * Lq + q0);
-      tma_load_2d(sm + OFF_QL, &P.tm_q_lo, q_full, x_col, b * Lq + q0);
-      int n = n_plan;
-      for (int pass = 0; pass < 2; ++pass) {
+          for (int k = 0; k < ATC_D / 16; ++k) umma_f16(tmem, dqh + 2 * k, dkl + 2 * k, idesc_s, 1u);
+          umma_commit(s_full);
+        };
+        if (pass == 0) {
+          mbar_arrive_expect_tx(q_full, 16384u);
+          tma_load_2d(sm + OFF_QH, &P.tm_q_hi, q_full, x_col, b * Lq + q0);
+          tma_load_2d(sm + OFF_QL, &P.tm_q_lo, q_full, x_col, b * Lq + q0);
+        }
         load_k(0, 0);
         if (n > 1) load_k(1, 1);
         load_v(0);
@@ -245,14 +248,12 @@ __global__ void __launch_bounds__(ATC_THREADS, 3) attention_tc_kernel(const __gr
           if (c + 2 < n) load_k(c + 2, c & 1);
           if (c + 1 < n) load_v(c + 1);
         }
-        // every row past the causal range must have seen a valid key; otherwise the whole tile is redone over all chunks
-        if (pass == 1 || !(p.causal && n_plan < n_all)) break;
-        if (!__syncthreads_or(0)) break;  // (vote of the softmax warps; this lane only joins the barrier)
-        n = n_all;
       }
-    } else {
-      // the other lanes of the control warp only join the block-wide vote (same trip count as lane 0)
-      if (p.causal && n_plan < n_all) __syncthreads_or(0);
+      __syncwarp();
+      // every row past the causal range must have seen a valid key; otherwise the whole tile is redone over all chunks
+      if (pass == 1 || !(p.causal && n_plan < n_all)) break;
+      if (!__syncthreads_or(0)) break;  // vote of the softmax warps; this warp only joins the barrier
+      n = n_all;
     }
   } else {
     // ======================================= softmax warps =======================================

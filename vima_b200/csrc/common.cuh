@@ -7,8 +7,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
-#ifndef VIMA_SPIN_LIMIT
-#define VIMA_SPIN_LIMIT (1u << 24)  // bounded mbarrier spin (each try_wait itself blocks for a HW time slice)
+#ifndef VIMA_WAIT_CYCLES
+#define VIMA_WAIT_CYCLES (3000000000ll)  // an mbarrier wait longer than ~2 s of SM clock is a protocol bug: trap instead of hanging the box
 #endif
 
 namespace vima {
@@ -167,10 +167,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug traps instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > VIMA_SPIN_LIMIT) {
-      printf("vima_b200: mbarrier timeout block %d thread %d\n", (int)blockIdx.x, (int)threadIdx.x);
+    if ((++spins & 1023u) == 0u && clock64() - t0 > VIMA_WAIT_CYCLES) {
+      printf("vima_b200: mbarrier timeout block (%d,%d,%d) thread %d bar %u parity %u\n", (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z,
+             (int)threadIdx.x, smem_u32(bar), parity);
       __trap();
     }
   }
