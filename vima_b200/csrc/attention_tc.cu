@@ -148,6 +148,10 @@ __global__ void __launch_bounds__(ATC_THREADS, 3) attention_tc_kernel(const __gr
     const int last_key = min(Lk - 1, q0 + rows_here - 1 + qp0);
     n_plan = last_key / ATC_KC + 1;
   }
+  // Pass 1 skips work that only matters for rows whose causally visible keys are all padded (chunks past the tile's diagonal, and
+  // inside the plan the chunks that are entirely hidden from a warp).  If any such skip can happen, the block votes afterwards and
+  // redoes the tile without shortcuts when some row is still "undone".
+  const bool may_rerun = p.causal && ((n_all - 1) * ATC_KC > q0 + qp0 + 31);
 
   if ((sbase & 1023u) != 0u) {  // the swizzled tiles assume a 1024-byte aligned window (no static shared memory in this kernel)
     if (tid == 0) printf("vima_b200: attention_tc shared memory window is not 1024-byte aligned\n");
@@ -251,7 +255,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 3) attention_tc_kernel(const __gr
       }
       __syncwarp();
       // every row past the causal range must have seen a valid key; otherwise the whole tile is redone over all chunks
-      if (pass == 1 || !(p.causal && n_plan < n_all)) break;
+      if (pass == 1 || !may_rerun) break;
       if (!__syncthreads_or(0)) break;  // vote of the softmax warps; this warp only joins the barrier
       n = n_all;
     }
@@ -379,7 +383,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 3) attention_tc_kernel(const __gr
         mbar_wait(p_free, (g - 1) & 1u);  // the last PV has retired: O is complete
         tcgen05_fence_after();
       }
-      if (pass == 1 || !(p.causal && n_plan < n_all)) break;
+      if (pass == 1 || !may_rerun) break;
       const int undone = w_on && row < Lq && !(m_ref > EXIT_L2_TC);
       if (!__syncthreads_or(undone)) break;
       n = n_all;
