@@ -53,7 +53,8 @@ void vima_destroy(vima_ctx* ctx);
 const char* vima_last_error(vima_ctx* ctx);
 int vima_sm_count(vima_ctx* ctx);
 /* Kernel-selection options, initialised from the environment in vima_create (see "environment" above) and switchable per context:
- * key "attn" = "tc" | "mma";  "gemm_mode" = "2cta" | "mcast" | "1cta";  "epi_prefetch" = "1" | "0".  Unknown key/value: VIMA_E_INVALID. */
+ * key "attn" = "tc" | "mma";  "attn_tail" = "1" | "0" (the <= 8 query rows past the last full 128-row tile on the SIMT tail kernel);
+ * "gemm_mode" = "2cta" | "mcast" | "1cta";  "epi_prefetch" = "1" | "0".  Unknown key/value: VIMA_E_INVALID. */
 int vima_set_option(vima_ctx* ctx, const char* key, const char* value);
 /* sizeof() of the descriptor structs as THIS library was compiled (bindings check their mirror structs against these). */
 int vima_sizeof_gemm_desc(void);

@@ -403,15 +403,22 @@ def action_modes(logits: torch.Tensor) -> Dict[str, torch.Tensor]:
     return out
 
 
-def forward_action_token(sd: SD, actions: Dict[str, torch.Tensor]) -> torch.Tensor:
-    """VIMAPolicy.forward_action_token = ActionEmbedding(_de_discretize_actions(a)), vima_policy.py:261-262,
-    301-322; vima/nn/action_embd/action_embd.py:29-37,55-56."""
+def de_discretize_actions(actions: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """VIMAPolicy._de_discretize_actions, vima_policy.py:301-322: bin index / bin count as float32 (50 x-bins, 100 y-bins,
+    50 rotation bins: vima_policy.py:77-79).  Pinned bit-exact by tests/golden/dediscretize.npz (minted from the reference method)."""
     a = {k: v.float().clone() for k, v in actions.items()}
     for k in ("pose0_position", "pose1_position"):
         a[k][..., 0] = a[k][..., 0] / 50
         a[k][..., 1] = a[k][..., 1] / 100
     for k in ("pose0_rotation", "pose1_rotation"):
         a[k] = a[k] / 50
+    return a
+
+
+def forward_action_token(sd: SD, actions: Dict[str, torch.Tensor]) -> torch.Tensor:
+    """VIMAPolicy.forward_action_token = ActionEmbedding(_de_discretize_actions(a)), vima_policy.py:261-262,
+    301-322; vima/nn/action_embd/action_embd.py:29-37,55-56."""
+    a = de_discretize_actions(actions)
     feats = [mlp_seq(sd, f"action_encoder._embed_dict.{k}._layer.", a[k], (0, 3)) for k in sorted(a.keys())]
     return linear(torch.cat(feats, dim=-1), sd["action_encoder._post_layer.weight"], sd["action_encoder._post_layer.bias"])
 

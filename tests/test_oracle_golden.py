@@ -115,3 +115,16 @@ def test_t5_bucket_table_matches_hf():
     ours = O.t5_relative_position_bucket(rel)
     hf = T5Attention._relative_position_bucket(rel, bidirectional=True, num_buckets=32, max_distance=128)
     assert ours.dtype == torch.int64 and torch.equal(ours, hf)
+
+
+def test_de_discretize_matches_reference_fixture():
+    """oracle.de_discretize_actions vs the fixture minted from the unmodified VIMAPolicy._de_discretize_actions
+    (tests/golden/make_dediscretize_golden.py; vima_policy.py:301-322): bit-exact over every bin index of every head."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "dediscretize.npz"))
+    keys = ["pose0_position", "pose0_rotation", "pose1_position", "pose1_rotation"]
+    got = O.de_discretize_actions({k: torch.from_numpy(g[f"in.{k}"]) for k in keys})
+    for k in keys:
+        assert got[k].dtype == torch.float32
+        assert np.array_equal(got[k].numpy(), g[f"out.{k}"]), k

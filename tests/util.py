@@ -43,6 +43,14 @@ def max_rel(expected, actual, floor=1e-3) -> float:
     return float(np.max(np.abs(a - e) / np.maximum(np.abs(e), floor * max(np.abs(e).max(), 1e-30))))
 
 
+def allclose_ratio(expected, actual, rtol=1e-3, atol_frac=1e-4) -> float:
+    """max |a - e| / (atol + rtol*|e|) with atol = atol_frac * max|e|: <= 1 means numpy.allclose(a, e, rtol, atol) holds."""
+    e = np.asarray(expected, dtype=np.float64)
+    a = np.asarray(actual, dtype=np.float64)
+    atol = atol_frac * max(np.abs(e).max(), 1e-30)
+    return float(np.max(np.abs(a - e) / (atol + rtol * np.abs(e))))
+
+
 def assert_close(name, expected, actual, tol):
     r = rel_l2(expected, actual)
     assert np.isfinite(np.asarray(actual, dtype=np.float64)).all(), f"{name}: non-finite values"

@@ -4,9 +4,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from vima_b200 import _C
 ctx = _C.Context.get(torch.device("cuda", 0))
-B, H, D, L, Lp = int(os.environ.get("AB_B", 256)), 24, 32, 263, 256
+B, H, D, L, Lp = int(os.environ.get("AB_B", 256)), 24, 32, int(os.environ.get("AB_L", 263)), 256
 E = H * D
-for split in (0, 1):
+for split in [int(x) for x in os.environ.get("AB_SPLIT", "0,1").split(",")]:
     for name, Lq, Lk, causal in (("self causal", L, L, True), ("cross", L, Lp, False)):
         mk = lambda r, c: torch.randint(-3000, 3000, (r, c), dtype=torch.int16, device="cuda")
         if causal:

@@ -19,7 +19,8 @@ shapes = [  # (name, N_acc, K, glu, epilogue)
 ]
 only = os.environ.get("GB_ONLY")
 reps = int(os.environ.get("GB_REPS", 3))
-for split in (0, 1, 2):
+splits = [int(x) for x in os.environ.get("GB_SPLIT", "0,1,2").split(",")]
+for split in splits:
     for name, N, K, glu, epi in shapes:
         if only and only not in name: continue
         a_hi = torch.randint(-2000, 2000, (M, K), dtype=torch.int16, device="cuda"); a_lo = torch.randint(-50, 50, (M, K), dtype=torch.int16, device="cuda") if split == 1 else None

@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(256, (D == 32) ? 2 : 1) attention_kernel(const
   const int kvb = p.kv_batch_rows ? p.kv_batch_rows : Lk;
   const int mld = p.mask_ld ? p.mask_ld : Lk;
   const int qp0 = p.q_pos0;
+  const int qbr = p.q_batch_rows ? p.q_batch_rows : Lq;
   // ---- stage K (row-major) and V (transposed) of this (b, h) in shared memory ----
   constexpr int CH = D / 8;  // 16-byte chunks per row
   for (int idx = tid; idx < Lk_pad * CH; idx += 256) {
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(256, (D == 32) ? 2 : 1) attention_kernel(const
         const int c = ks * 16 + 2 * t + ((e & 2) ? 8 : 0);
         uint32_t vh = 0, vl = 0;
         if (r < Lq) {
-          const size_t off = (size_t)(b * Lq + r) * p.ldq + h * D + c;
+          const size_t off = ((size_t)b * qbr + r) * p.ldq + h * D + c;
           vh = __ldg(reinterpret_cast<const uint32_t*>(p.q_hi + off));
           if (SPLIT) vl = __ldg(reinterpret_cast<const uint32_t*>(p.q_lo + off));
         }
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(256, (D == 32) ? 2 : 1) attention_kernel(const
         if (r >= Lq) continue;
         const float x0 = o[n][2 * half] * (half ? inv1 : inv0), x1 = o[n][2 * half + 1] * (half ? inv1 : inv0);
         pack_split<DT>(x0, x1, hi, lo);
-        const size_t off = (size_t)(b * Lq + r) * p.ldo + c;
+        const size_t off = ((size_t)b * qbr + r) * p.ldo + c;
         *reinterpret_cast<uint32_t*>(p.o_hi + off) = hi;
         if (p.o_lo) *reinterpret_cast<uint32_t*>(p.o_lo + off) = lo;
         if (p.o_lo8) {  // e4m3 cross-term views for an "f16f8" consumer GEMM
@@ -294,7 +295,7 @@ __global__ void __launch_bounds__(256, (D == 32) ? 2 : 1) attention_kernel(const
           unsigned short l8, h8;
           asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(l8) : "f"((x1 - hf.y) * F8_ACT_LO_SCALE), "f"((x0 - hf.x) * F8_ACT_LO_SCALE));
           asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(h8) : "f"(x1 * F8_ACT_HI_SCALE), "f"(x0 * F8_ACT_HI_SCALE));
-          const size_t off8 = (size_t)(b * Lq + r) * p.ldo8 + c;
+          const size_t off8 = ((size_t)b * qbr + r) * p.ldo8 + c;
           *reinterpret_cast<unsigned short*>(p.o_lo8 + off8) = l8;
           *reinterpret_cast<unsigned short*>(p.o_hi8 + off8) = h8;
         }

@@ -89,7 +89,8 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // one query row of the output: x = o * inv as (hi, lo) 16-bit pairs [+ e4m3 cross-term views for an "f16f8" consumer GEMM]
 template <int DT>
 __device__ __forceinline__ void store_row(const AttnParams& p, int b, int row, int h, const uint32_t (&o)[ATC_D], float inv) {
-  const size_t off = ((size_t)b * p.Lq + row) * p.ldo + h * ATC_D;
+  const size_t brow = (size_t)b * (p.q_batch_rows ? p.q_batch_rows : p.Lq) + row;
+  const size_t off = brow * p.ldo + h * ATC_D;
 #pragma unroll
   for (int c8 = 0; c8 < ATC_D / 8; ++c8) {
     uint32_t hi[4], lo[4];
@@ -101,7 +102,7 @@ __device__ __forceinline__ void store_row(const AttnParams& p, int b, int row, i
     *reinterpret_cast<uint4*>(p.o_hi + off + c8 * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     if (p.o_lo) *reinterpret_cast<uint4*>(p.o_lo + off + c8 * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     if (p.o_lo8) {
-      const size_t off8 = ((size_t)b * p.Lq + row) * p.ldo8 + h * ATC_D + c8 * 8;
+      const size_t off8 = brow * p.ldo8 + h * ATC_D + c8 * 8;
       uint32_t l8[2], h8[2];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
@@ -139,6 +140,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 3) attention_tc_kernel(const __gr
   const int kvb = p.kv_batch_rows ? p.kv_batch_rows : Lk;
   const int mld = p.mask_ld ? p.mask_ld : Lk;
   const int qp0 = p.q_pos0;
+  const int qbr = p.q_batch_rows ? p.q_batch_rows : Lq;
   const uint32_t sbase = smem_u32(sm);
   const int rows_here = min(ATC_BM, Lq - q0);
   const int n_act = (rows_here + 31) >> 5;  // softmax warps that own at least one real query row
@@ -223,8 +225,8 @@ __global__ void __launch_bounds__(ATC_THREADS, 3) attention_tc_kernel(const __gr
         };
         if (pass == 0) {
           mbar_arrive_expect_tx(q_full, 16384u);
-          tma_load_2d(sm + OFF_QH, &P.tm_q_hi, q_full, x_col, b * Lq + q0);
-          tma_load_2d(sm + OFF_QL, &P.tm_q_lo, q_full, x_col, b * Lq + q0);
+          tma_load_2d(sm + OFF_QH, &P.tm_q_hi, q_full, x_col, b * qbr + q0);
+          tma_load_2d(sm + OFF_QL, &P.tm_q_lo, q_full, x_col, b * qbr + q0);
         }
         load_k(0, 0);
         if (n > 1) load_k(1, 1);
@@ -437,9 +439,10 @@ cudaError_t launch_attention_tc(const AttnParams& p, void* encode_fn, cudaStream
   AttnTcParams P;
   P.a = p;
   const int kvb = p.kv_batch_rows ? p.kv_batch_rows : p.Lk;
+  const int qbr = p.q_batch_rows ? p.q_batch_rows : p.Lq;
   const int cols = p.H * ATC_D;
-  bool ok = make_map(encode_fn, &P.tm_q_hi, p.q_hi, p.dtype, (long long)p.B * p.Lq, cols, p.ldq, ATC_BM) &&
-            make_map(encode_fn, &P.tm_q_lo, p.q_lo, p.dtype, (long long)p.B * p.Lq, cols, p.ldq, ATC_BM) &&
+  bool ok = make_map(encode_fn, &P.tm_q_hi, p.q_hi, p.dtype, (long long)p.B * qbr, cols, p.ldq, ATC_BM) &&
+            make_map(encode_fn, &P.tm_q_lo, p.q_lo, p.dtype, (long long)p.B * qbr, cols, p.ldq, ATC_BM) &&
             make_map(encode_fn, &P.tm_k_hi, p.k_hi, p.dtype, (long long)p.B * kvb, cols, p.ldk, ATC_KC) &&
             make_map(encode_fn, &P.tm_k_lo, p.k_lo, p.dtype, (long long)p.B * kvb, cols, p.ldk, ATC_KC) &&
             make_map(encode_fn, &P.tm_v_hi, p.v_hi, p.dtype, (long long)p.B * kvb, cols, p.ldv, ATC_KC) &&
