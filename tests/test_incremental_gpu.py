@@ -36,9 +36,12 @@ def test_cached_steps_match_full_history(case_name, mode, tol):
                 full = pol.forward(obs_token=obs_tok[:t + 1], obs_mask=obs_msk[:t + 1], action_token=None if t == 0 else act_tok[:t],
                                    prompt_token=p_tok, prompt_token_mask=p_msk)[-1:]
                 assert step.shape == (1, B, E)
-                # same kernels, same per-row arithmetic; only the attention tiling over the prefix differs
+                # same GEMM / LayerNorm kernels and per-row arithmetic; the attention of these rows runs on the tcgen05 kernel in the
+                # cached step and -- when the full history leaves <= 8 rows past its last 128-row tile (t = 3: L = 131) -- on the
+                # fp32 SIMT tail kernel in the re-forward: two roundings of the same product.  f16x3 keeps that at the 1e-6 level;
+                # in f16f8 the e4m3 cross-term views of the following GEMMs re-quantise the difference (measured 1.4e-5)
                 d = rel_l2(full.cpu(), step.cpu())
-                assert d < 2e-6, (t, d)
+                assert d < (2e-6 if mode == "f16x3" else 5e-5), (t, d)
             assert cache.L == T * Q + T - 1
             # and the last step against the CPU oracle's full forward on the same tokens
             ref = O.policy_forward(sd, obs_tok.cpu(), obs_msk.cpu(), None if act_tok is None else act_tok.cpu(), p_tok.cpu(), p_msk.cpu(),

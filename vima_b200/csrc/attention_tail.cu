@@ -80,35 +80,42 @@ __global__ void __launch_bounds__(TAIL_WARPS * 32) attention_tail_kernel(const A
 #pragma unroll
   for (int i = 0; i < TAIL_NT; ++i) mx[i] = -INFINITY;
   const int pos0 = row0 + p.q_pos0;  // key position of tail row 0 (causal)
+  // raw (hi, lo) words of this lane's key row; the NEXT batch's rows are requested as soon as the current ones are converted, so the
+  // L2 round trip overlaps the 128 packed FMAs of the batch in hand
+  uint4 kh[4], kl[4];
+  auto load_k = [&](int j) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { kh[c] = make_uint4(0u, 0u, 0u, 0u); kl[c] = kh[c]; }
+    if (j < Lk) {
+      const size_t rk = ((size_t)b * kvb + j) * p.ldk + h * TAIL_D;
+      const uint4* ph = reinterpret_cast<const uint4*>(p.k_hi + rk);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) kh[c] = __ldg(ph + c);
+      if (p.k_lo) {
+        const uint4* pl = reinterpret_cast<const uint4*>(p.k_lo + rk);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) kl[c] = __ldg(pl + c);
+      }
+    }
+  };
+  load_k(lane);
   for (int j0 = 0; j0 < lk_pad; j0 += 32) {
     const int j = j0 + lane;
     const bool valid = j < Lk;
     unsigned long long kf[TAIL_D / 2];
-    float madd = -INFINITY;  // beyond the sequence: excluded
-    if (valid) {
-      const size_t rk = ((size_t)b * kvb + j) * p.ldk + h * TAIL_D;
-      const uint4* ph = reinterpret_cast<const uint4*>(p.k_hi + rk);
-      const uint4* pl = reinterpret_cast<const uint4*>(p.k_lo + rk);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint4 a = __ldg(ph + c);
-        const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
-        uint32_t lw[4] = {0u, 0u, 0u, 0u};
-        if (p.k_lo) {
-          const uint4 l = __ldg(pl + c);
-          lw[0] = l.x; lw[1] = l.y; lw[2] = l.z; lw[3] = l.w;
-        }
+    for (int c = 0; c < 4; ++c) {
+      const uint32_t aw[4] = {kh[c].x, kh[c].y, kh[c].z, kh[c].w};
+      const uint32_t lw[4] = {kl[c].x, kl[c].y, kl[c].z, kl[c].w};
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 x = unpack2<DT>(aw[e]), y = unpack2<DT>(lw[e]);
-          kf[c * 4 + e] = pack2(x.x + y.x, x.y + y.y);
-        }
+      for (int e = 0; e < 4; ++e) {
+        const float2 x = unpack2<DT>(aw[e]), y = unpack2<DT>(lw[e]);
+        kf[c * 4 + e] = pack2(x.x + y.x, x.y + y.y);
       }
-      madd = (p.key_mask == nullptr || p.key_mask[(size_t)b * mld + j]) ? 0.f : FP32_MIN_TL;
-    } else {
-#pragma unroll
-      for (int e = 0; e < TAIL_D / 2; ++e) kf[e] = 0ull;
     }
+    if (j0 + 32 < lk_pad) load_k(j + 32);
+    float madd = -INFINITY;  // beyond the sequence: excluded
+    if (valid) madd = (p.key_mask == nullptr || p.key_mask[(size_t)b * mld + j]) ? 0.f : FP32_MIN_TL;
     float y[TAIL_NT];
 #pragma unroll
     for (int i = 0; i < TAIL_NT; ++i) {
@@ -158,21 +165,33 @@ __global__ void __launch_bounds__(TAIL_WARPS * 32) attention_tail_kernel(const A
   unsigned long long acc[TAIL_NT][2];
 #pragma unroll
   for (int i = 0; i < TAIL_NT; ++i) { acc[i][0] = 0ull; acc[i][1] = 0ull; }
-  for (int j = kg; j < Lk; j += 4) {
-    const size_t rv = ((size_t)b * kvb + j) * p.ldv + h * TAIL_D + dg * 4;
-    const uint2 vh = __ldg(reinterpret_cast<const uint2*>(p.v_hi + rv));
-    uint2 vl = make_uint2(0u, 0u);
-    if (p.v_lo) vl = __ldg(reinterpret_cast<const uint2*>(p.v_lo + rv));
-    const float2 h0 = unpack2<DT>(vh.x), l0 = unpack2<DT>(vl.x), h1 = unpack2<DT>(vh.y), l1 = unpack2<DT>(vl.y);
-    const unsigned long long v01 = pack2(h0.x + l0.x, h0.y + l0.y), v23 = pack2(h1.x + l1.x, h1.y + l1.y);
-    const float4* cell = reinterpret_cast<const float4*>(sc + (size_t)j * TAIL_NT);
-    const float4 a = cell[0], c = cell[1];
-    const float w[TAIL_NT] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+  for (int j = kg; j < Lk; j += 16) {  // 4 keys per lane group per trip: their loads are all in flight before the first FMA
+    uint2 vh[4], vl[4];
 #pragma unroll
-    for (int i = 0; i < TAIL_NT; ++i) {
-      const unsigned long long ww = pack2(w[i], w[i]);
-      ffma2(acc[i][0], ww, v01);
-      ffma2(acc[i][1], ww, v23);
+    for (int u = 0; u < 4; ++u) {
+      const int jj = j + 4 * u;
+      vh[u] = make_uint2(0u, 0u); vl[u] = vh[u];
+      if (jj < Lk) {
+        const size_t rv = ((size_t)b * kvb + jj) * p.ldv + h * TAIL_D + dg * 4;
+        vh[u] = __ldg(reinterpret_cast<const uint2*>(p.v_hi + rv));
+        if (p.v_lo) vl[u] = __ldg(reinterpret_cast<const uint2*>(p.v_lo + rv));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int jj = j + 4 * u;
+      if (jj >= Lk) break;
+      const float2 h0 = unpack2<DT>(vh[u].x), l0 = unpack2<DT>(vl[u].x), h1 = unpack2<DT>(vh[u].y), l1 = unpack2<DT>(vl[u].y);
+      const unsigned long long v01 = pack2(h0.x + l0.x, h0.y + l0.y), v23 = pack2(h1.x + l1.x, h1.y + l1.y);
+      const float4* cell = reinterpret_cast<const float4*>(sc + (size_t)jj * TAIL_NT);
+      const float4 a = cell[0], c = cell[1];
+      const float w[TAIL_NT] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+      for (int i = 0; i < TAIL_NT; ++i) {
+        const unsigned long long ww = pack2(w[i], w[i]);
+        ffma2(acc[i][0], ww, v01);
+        ffma2(acc[i][1], ww, v23);
+      }
     }
   }
   // fold the 4 key groups (lanes differing in bits 3 and 4); afterwards every lane holds the full sums of its 4 dims

@@ -110,7 +110,8 @@ __device__ __forceinline__ void split4(const float4& y, uint2& hi, uint2& lo) { 
 // 64-bit 16-bit pairs), issued after the sub-chunk's global loads are already in flight.
 template <class E>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_row, const float* __restrict__ sb, float* __restrict__ st,
-                                              int lane, int ehalf, int row_base, int tn, int bn_out, int n_out) {
+                                              int lane, int ehalf, int row_base, int tn, int bn_out, int n_out, uint64_t* acc_full,
+                                              uint32_t acc_phase) {
   const bool glu = E::GENERIC ? (p.glu != 0) : E::GLU;
   const bool has_mul = E::GENERIC ? (p.mul != nullptr) : E::MUL;
   const bool has_res = E::GENERIC ? (p.residual != nullptr) : E::RES;
@@ -148,19 +149,34 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_ro
       }
     }
   }
-  for (int j0 = ehalf * 32; j0 < bn_out; j0 += 64) {
+  // This warp's 16-column sub-chunks: s -> columns ehalf*32 + (s/2)*64 + (s%2)*16.  The multiplier / residual rows of sub-chunk
+  // s+1 are requested before sub-chunk s is processed (one sub-chunk of register prefetch): their latency -- the largest single
+  // stall of the residual-carrying N = 768 GEMMs in the round-2 ncu source view -- overlaps the TMEM read, the transpose and the
+  // stores of the sub-chunk in hand.
+  const int n_sub = ((bn_out - ehalf * 32 + 63) / 64) * 2;
+  auto sub_j = [&](int s) { return ehalf * 32 + (s >> 1) * 64 + (s & 1) * 16; };
+  auto load_mr = [&](int j, float4 (&mm_)[4], float4 (&rr_)[4]) {
+    const int col = tn * bn_out + j + kc * 4;
+    const bool col_ok = col < n_out;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int row = row_base + it * 8 + sub;
+      const bool ok = col_ok && row < p.M;
+      if (has_mul) mm_[it] = ok ? __ldg(reinterpret_cast<const float4*>(p.mul + (size_t)row * p.ld_mul + col)) : make_float4(1.f, 1.f, 1.f, 1.f);
+      if (has_res) rr_[it] = ok ? __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)row * p.ld_res + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  float4 mm[4], rr[4], mm_n[4], rr_n[4];
+  if (n_sub > 0) load_mr(sub_j(0), mm, rr);  // in flight while the accumulator tile is still being produced
+  mbar_wait(acc_full, acc_phase);
+  tcgen05_fence_after();
+  {
 #pragma unroll 1
-    for (int j = j0; j < j0 + 32; j += 16) {
+    for (int s = 0; s < n_sub; ++s) {
+      const int j = sub_j(s);
       const int col = tn * bn_out + j + kc * 4;
       const bool col_ok = col < n_out;  // n_out % 4 == 0 (checked on the host)
-      float4 mm[4], rr[4];
-#pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const int row = row_base + it * 8 + sub;
-        const bool ok = col_ok && row < p.M;
-        if (has_mul) mm[it] = ok ? __ldg(reinterpret_cast<const float4*>(p.mul + (size_t)row * p.ld_mul + col)) : make_float4(1.f, 1.f, 1.f, 1.f);
-        if (has_res) rr[it] = ok ? __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)row * p.ld_res + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      if (s + 1 < n_sub) load_mr(sub_j(s + 1), mm_n, rr_n);
       uint32_t v[16];
       tmem_ld_32x16(t_row + j, v);
       float x[16];
@@ -272,6 +288,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_ro
         }
       }
       __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        if (has_mul) mm[it] = mm_n[it];
+        if (has_res) rr[it] = rr_n[it];
+      }
     }
   }
   if (stats) {
@@ -540,10 +561,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         }
       }
       named_bar_sync(1, 32 * GEMM_EPI_WARPS);
-      mbar_wait(&tmem_full[ab], aphase);
-      tcgen05_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(we * 32) << 16) + (uint32_t)(ab * 256);
-      epilogue_tile<E>(p, t_row, sb, st, lane, ehalf, m0 + we * 32, tn, bn_out, n_out);
+      epilogue_tile<E>(p, t_row, sb, st, lane, ehalf, m0 + we * 32, tn, bn_out, n_out, &tmem_full[ab], aphase);  // waits for the accumulator
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) {

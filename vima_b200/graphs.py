@@ -67,6 +67,12 @@ class GraphedStep:
         self.replays += 1
         return self.static_out
 
+    def load_inputs(self, src):
+        """Copy `src` (same nest; pinned host or device tensors) straight into the graph's static input buffers, asynchronously on
+        the current stream; follow with `self(self.static_in)` to replay without a second device-to-device copy."""
+        _map(lambda dst, s: dst.copy_(s, non_blocking=True), self.static_in, src)
+        return self.static_in
+
     def describe(self) -> dict:
         return {"vima_kernels_per_replay": int(self.kernels_per_replay),
                 "note": "the step is captured once (torch.cuda.CUDAGraph) and replayed; inputs are copied into static buffers"}
