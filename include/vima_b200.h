@@ -24,7 +24,7 @@
  *     VIMA_E_INVALID, so growing a descriptor never makes an old binding read or write through garbage.
  *     `vima_sizeof_*()` report the library's own sizes (bindings assert equality at load time).
  *   - the calling thread's current CUDA device is saved and restored around every call.
- *   - environment (read ONCE, in vima_create): VIMA_B200_ATTN = tc (default) | mma;  VIMA_B200_ATTN_TAIL = fused (default) | kernel | off;  VIMA_B200_GEMM_MODE = 2cta (default) |
+ *   - environment (read ONCE, in vima_create): VIMA_B200_ATTN = tc (default) | mma;  VIMA_B200_ATTN_TAIL = kernel (default) | off;  VIMA_B200_GEMM_MODE = 2cta (default) |
  *     mcast | 1cta;  VIMA_B200_EPI_PREFETCH = 0 (default) | 1.
  */
 #ifndef VIMA_B200_H
@@ -53,8 +53,8 @@ void vima_destroy(vima_ctx* ctx);
 const char* vima_last_error(vima_ctx* ctx);
 int vima_sm_count(vima_ctx* ctx);
 /* Kernel-selection options, initialised from the environment in vima_create (see "environment" above) and switchable per context:
- * key "attn" = "tc" | "mma";  "attn_tail" = "fused" | "kernel" | "off" (the <= 8 query rows past the last full 128-row tile: SIMT
- * routine inside the tcgen05 kernel, in a launch of its own, or one more tcgen05 tile);
+ * key "attn" = "tc" | "mma";  "attn_tail" = "kernel" | "off" (the <= 8 query rows past the last full 128-row tile: SIMT tail
+ * kernel, or one more tcgen05 tile);
  * "gemm_mode" = "2cta" | "mcast" | "1cta";  "epi_prefetch" = "1" | "0".  Unknown key/value: VIMA_E_INVALID. */
 int vima_set_option(vima_ctx* ctx, const char* key, const char* value);
 /* sizeof() of the descriptor structs as THIS library was compiled (bindings check their mirror structs against these). */

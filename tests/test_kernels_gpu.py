@@ -243,17 +243,16 @@ def ref_attention(q, k, v, scale, causal, key_mask, bias):
     return torch.matmul(torch.softmax(s, -1), v)
 
 
-@pytest.fixture(params=["mma", "tc", "tc+tail_kernel", "tc+tail_off"])
+@pytest.fixture(params=["mma", "tc", "tc+tail_off"])
 def attn_impl(request, ctx):
     """Both attention kernels: mma.sync (attention.cu) and tcgen05 (attention_tc.cu; shapes it does not take fall back), the latter
-    with its three treatments of the <= 8 rows past the last full 128-row tile: SIMT routine fused into the kernel (default), in a
-    launch of its own, or one more tcgen05 tile."""
+    with its two treatments of the <= 8 rows past the last full 128-row tile: the SIMT tail kernel (default) or one more tcgen05 tile."""
     impl, _, tail = request.param.partition("+tail_")
     ctx.set_option("attn", impl)
-    ctx.set_option("attn_tail", tail or "fused")
+    ctx.set_option("attn_tail", tail or "kernel")
     yield request.param
     ctx.set_option("attn", "tc")
-    ctx.set_option("attn_tail", "fused")
+    ctx.set_option("attn_tail", "kernel")
 
 
 @pytest.mark.parametrize("split", [False, True])

@@ -173,7 +173,7 @@ class Context:
             raise RuntimeError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")
 
     def set_option(self, key: str, value: str) -> None:
-        """Kernel selection of this context: attn = tc | mma, attn_tail = fused | kernel | off, gemm_mode = 2cta | mcast | 1cta,
+        """Kernel selection of this context: attn = tc | mma, attn_tail = kernel | off, gemm_mode = 2cta | mcast | 1cta,
         epi_prefetch = 1 | 0."""
         self._ck(self.lib.vima_set_option(self.h, key.encode(), str(value).encode()), "set_option")
 

@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 LIB_PATH = os.path.join(OUT_DIR, "libvima_b200.so")
 SOURCES = ["api.cu", "gemm_tc_f16.cu", "gemm_tc_bf16.cu", "norm.cu", "attention.cu", "attention_tc.cu", "attention_tail.cu", "gemm_simt.cu", "misc.cu", "prepare.cu"]
-HEADERS = ["common.cuh", "kernels.h", "attention_tail.cuh", "gemm_tc.cuh", "gemm_tc_variants.cuh", os.path.join("..", "..", "include", "vima_b200.h")]
+HEADERS = ["common.cuh", "kernels.h", "gemm_tc.cuh", "gemm_tc_variants.cuh", os.path.join("..", "..", "include", "vima_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--expt-relaxed-constexpr",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",

@@ -22,8 +22,8 @@ struct vima_ctx {
   bool gemm_attr_set;
   // environment, read once in vima_create
   int attn_tc;       // VIMA_B200_ATTN: tc (1, default) | mma (0)
-  int attn_tail;     // VIMA_B200_ATTN_TAIL: the <= 8 rows past the last full 128-row tile: 2 = "fused" (default; SIMT routine inside
-                     // the tcgen05 kernel), 1 = "kernel" (launch of its own), 0 = "off" (one more tcgen05 tile)
+  int attn_tail;     // VIMA_B200_ATTN_TAIL: the <= 8 rows past the last full 128-row tile: 1 = "kernel" (default; SIMT tail kernel),
+                     // 0 = "off" (one more tcgen05 tile)
   int gemm_mode;     // VIMA_B200_GEMM_MODE: 1cta (0) | mcast (1) | 2cta (2, default)
   int epi_prefetch;  // VIMA_B200_EPI_PREFETCH: L2 prefetch of the next tile's residual / multiplier rows (default 0: A/B in profiles/r2_summary.md)
 };
@@ -100,7 +100,6 @@ int vima_set_option(vima_ctx* c, const char* key, const char* value) {
     if (!strcmp(value, "tc")) { c->attn_tc = 1; return VIMA_OK; }
     if (!strcmp(value, "mma")) { c->attn_tc = 0; return VIMA_OK; }
   } else if (!strcmp(key, "attn_tail")) {
-    if (!strcmp(value, "fused")) { c->attn_tail = 2; return VIMA_OK; }
     if (!strcmp(value, "kernel")) { c->attn_tail = 1; return VIMA_OK; }
     if (!strcmp(value, "off")) { c->attn_tail = 0; return VIMA_OK; }
   } else if (!strcmp(key, "gemm_mode")) {
@@ -135,7 +134,7 @@ int vima_create(vima_ctx** out, int device) {
     return VIMA_E_CUDA;
   }
   c->encode_tiled = fn;
-  c->attn_tc = 1; c->attn_tail = 2; c->gemm_mode = 2; c->epi_prefetch = 0;
+  c->attn_tc = 1; c->attn_tail = 1; c->gemm_mode = 2; c->epi_prefetch = 0;
   if (const char* e = getenv("VIMA_B200_ATTN")) vima_set_option(c, "attn", e);  // unknown values keep the default
   if (const char* e = getenv("VIMA_B200_ATTN_TAIL")) vima_set_option(c, "attn_tail", e);
   if (const char* e = getenv("VIMA_B200_GEMM_MODE")) vima_set_option(c, "gemm_mode", e);
@@ -401,7 +400,7 @@ int vima_attention(vima_ctx* c, const vima_attn_desc* d_in, void* stream) {
   p.B = d->B; p.H = d->H; p.Lq = d->Lq; p.Lk = d->Lk; p.D = d->D;
   p.scale = d->scale; p.causal = d->causal; p.split = split; p.dtype = d->dtype;
   p.o_lo8 = (unsigned char*)d->o_lo8; p.o_hi8 = (unsigned char*)d->o_hi8; p.ldo8 = d->ldo8;
-  p.kv_batch_rows = d->kv_batch_rows; p.mask_ld = d->mask_ld; p.q_pos0 = d->q_pos0; p.q_batch_rows = 0; p.tail_row0 = 0; p.tail_rows = 0;
+  p.kv_batch_rows = d->kv_batch_rows; p.mask_ld = d->mask_ld; p.q_pos0 = d->q_pos0; p.q_batch_rows = 0;
   if ((d->kv_batch_rows && d->kv_batch_rows < d->Lk) || (d->mask_ld && d->mask_ld < d->Lk) || d->q_pos0 < 0)
     return fail(c, VIMA_E_INVALID, "attention: kv_batch_rows / mask_ld must cover Lk, q_pos0 >= 0");
   if ((p.o_lo8 == nullptr) != (p.o_hi8 == nullptr) || (p.o_lo8 && ((p.ldo8 & 1) || d->dtype != DT_F16)))
@@ -410,18 +409,15 @@ int vima_attention(vima_ctx* c, const vima_attn_desc* d_in, void* stream) {
   // VIMA_B200_ATTN=mma (read once in vima_create) forces the latter.  Both are covered by the kernel tests.
   if (c->attn_tc && attention_tc_supported(p)) {
     // the tcgen05 kernel works on 128-row query tiles: a few rows past the last full tile (7 of 263, 8 of 392) would hold a CTA slot
-    // for the whole key range with one warp of four at work -- they are computed by the SIMT routine of attention_tail.cuh instead,
-    // inside the CTA of the last full tile ("fused") or in a launch of their own ("kernel")
+    // for the whole key range with one warp of four at work -- they go to the SIMT tail kernel instead (attention_tail.cu).
+    // Measured per decoder layer at the benchmark shape (self + cross, B = 256, L = 263): 1.71 ms with one more tcgen05 tile,
+    // 1.58 ms with the tail kernel; running the same routine inside the CTA of the last full tile was slower than both (1.80 ms:
+    // it extends the lifetime of a CTA that holds TMEM and 76 KB of shared memory) and was dropped (profiles/r2i_*).
     const int tail = p.Lq % 128;
     if (c->attn_tail && p.Lq > 128 && tail >= 1 && tail <= ATTN_TAIL_MAX_ROWS) {
       AttnParams body = p;
       body.Lq = p.Lq - tail;
       body.q_batch_rows = p.Lq;
-      if (c->attn_tail == 2) {
-        body.tail_row0 = p.Lq - tail;
-        body.tail_rows = tail;
-        LAUNCHED(c, launch_attention_tc(body, c->encode_tiled, (cudaStream_t)stream), "attention_tc");
-      }
       cudaError_t e_ = launch_attention_tc(body, c->encode_tiled, (cudaStream_t)stream);
       if (e_ != cudaSuccess) return cuda_fail(c, e_, "attention_tc");
       c->launches++;

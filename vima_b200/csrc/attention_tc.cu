@@ -20,7 +20,7 @@
 // weight exp(-1e4 - m) == 0 exactly in fp32 once m > -1e4 + 104, so stopping there is bit-compatible with the reference's
 // full-width softmax.  If some row has only seen padded keys by then (m still <= -9000), the tile is re-run over every chunk
 // with the exact formulas (rare: the first history slot is always valid in VIMA's data).
-#include "attention_tail.cuh"
+#include "kernels.h"
 
 namespace vima {
 
@@ -397,12 +397,6 @@ __global__ void __launch_bounds__(ATC_THREADS, 3) attention_tc_kernel(const __gr
       tmem_ld_wait();
       if (row < Lq) store_row<DT>(p, b, row, h, ov, 1.0f / l_run);
     }
-    // ---- the few rows past the last full tile (attention_tail.cuh): this CTA's four softmax warps, K / V still L2-hot ----
-    if (p.tail_rows > 0 && blockIdx.x == gridDim.x - 1) {
-      // every tcgen05.mma that read the P buffers has retired (each warp waited for the last p_free): the region is free scratch
-      named_bar_sync(1, 128);
-      attention_tail_rows<DT, 4>(p, b, h, p.tail_row0, p.tail_rows, (Lk + 31) & ~31, reinterpret_cast<float*>(sm + OFF_PH), tid, 1);
-    }
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -440,11 +434,8 @@ bool attention_tc_supported(const AttnParams& p) {
          p.Lk <= ATC_MAX_LK;
 }
 
-static_assert(attention_tail_scratch_floats(ATC_MAX_LK, 4) * 4 <= OFF_MASK - OFF_PH, "the tail scratch lives in the P buffers");
-
 cudaError_t launch_attention_tc(const AttnParams& p, void* encode_fn, cudaStream_t stream) {
   if (p.B == 0 || p.Lq == 0) return cudaSuccess;
-  if (p.tail_rows < 0 || p.tail_rows > ATTN_TAIL_MAX_ROWS || (p.tail_rows > 0 && (p.Lq % ATC_BM) != 0)) return cudaErrorInvalidValue;
   AttnTcParams P;
   P.a = p;
   const int kvb = p.kv_batch_rows ? p.kv_batch_rows : p.Lk;

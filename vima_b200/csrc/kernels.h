@@ -35,8 +35,6 @@ struct AttnParams {
   int mask_ld;                                 // row pitch of key_mask, 0 = Lk
   int q_pos0;                                  // causal: query row i sits at key position q_pos0 + i (incremental decode)
   int q_batch_rows;                            // rows between consecutive batch elements in q / o (>= Lq), 0 = Lq
-  int tail_row0, tail_rows;                    // attention_tc only: rows [tail_row0, +tail_rows) (<= 8, beyond Lq) are computed by the
-                                               // CTA of the last full tile with the SIMT routine of attention_tail.cuh; 0 rows = none
 };
 constexpr int ATTN_TAIL_MAX_ROWS = 8;          // attention_tail.cu: query rows per (batch, head) the SIMT tail kernel takes
 cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream);
