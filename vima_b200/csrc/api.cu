@@ -125,7 +125,8 @@ int vima_create(vima_ctx** out, int device) {
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
   c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
-  if (cudaSetDevice(device) != cudaSuccess) { delete c; return VIMA_E_CUDA; }
+  DeviceGuard guard;  // the calling thread's current device is restored on every return path below
+  if (guard.enter(device) != cudaSuccess) { delete c; return VIMA_E_CUDA; }
   cudaFree(0);
   cudaDriverEntryPointQueryResult q;
   void* fn = nullptr;
