@@ -385,20 +385,32 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline_subprocess(args):
-    """Runs `bench.py --impl reference` (the code the driver's reference arm runs) in a fresh process: one code path, one number."""
+def cpu_baseline_start(args):
+    """Starts `bench.py --impl reference` (the code the driver's reference arm runs) in a fresh process: one code path, one number.
+    The child sees no GPU and uses its own fixed thread count; it runs while this process does the GPU-resident `gpu_eager` leg (whose
+    host side is confined to a few threads meanwhile), which takes about a minute off the default run."""
     cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload, "--steps", "5", "--warmup", "2",
            "--cpu-episodes", str(args.cpu_episodes)] + (["--ragged"] if args.ragged else []) + (["--batch", str(args.batch)] if args.batch else []) \
         + (["--cpu-threads", str(args.cpu_threads)] if args.cpu_threads else [])
     env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
     env["CUDA_VISIBLE_DEVICES"] = ""
     try:
-        r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
-        for ln in reversed(r.stdout.strip().splitlines()):
+        return subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)[:400]}
+
+
+def cpu_baseline_collect(proc):
+    if isinstance(proc, dict):
+        return proc
+    try:
+        out, err = proc.communicate(timeout=900)
+        for ln in reversed(out.strip().splitlines()):
             if ln.startswith("{"):
                 return json.loads(ln)["cpu_baseline"]
-        return {"error": (r.stderr or r.stdout)[-400:]}
+        return {"error": (err or out)[-400:]}
     except Exception as e:  # noqa: BLE001
+        proc.kill()
         return {"error": repr(e)[:400]}
 
 
@@ -460,9 +472,11 @@ def encode_prompt(policy, wl: Workload, dev):
     policy.forward_prompt_assembly(pr_in)  # warm (weight packing)
     torch.cuda.synchronize()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    torch.cuda.nvtx.range_push("prompt")  # ncu --nvtx-include "prompt/": the once-per-episode prompt encode on its own
     e0.record()
     tok, msk = policy.forward_prompt_assembly(pr_in)
     e1.record(); torch.cuda.synchronize()
+    torch.cuda.nvtx.range_pop()
     return tok, msk, e0.elapsed_time(e1)
 
 
@@ -667,6 +681,12 @@ def run_ours(args):
                 incr_ms = e4.elapsed_time(e5)
                 del cache
 
+        # ---- the reference on the host cores (child process, no GPU), started now so that it overlaps the eager leg below ----
+        cpu_proc = None
+        if not args.no_cpu_baseline and world == 1:
+            cpu_proc = cpu_baseline_start(args)
+            torch.set_num_threads(4)  # this process's host work from here on is set-up code; the child owns its 32 threads
+
         # ---- same-GPU comparator: the unmodified reference in PyTorch eager (rank 0, N=1 only) ----
         eager = None
         if world == 1 and not args.no_gpu_eager:
@@ -750,8 +770,8 @@ def run_ours(args):
                                            "decoder + heads + action embed per step; obs tokens precomputed); same predictions as the full re-forward"}
         if eager is not None:
             line["gpu_eager"] = eager
-        if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline_subprocess(args)
+        if cpu_proc is not None:
+            line["cpu_baseline"] = cpu_baseline_collect(cpu_proc)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -7,12 +7,16 @@
 namespace vima {
 
 constexpr int ST = 64;   // tile edge
-constexpr int SK = 16;   // k step
+constexpr int SK = 32;   // k step
+constexpr int SIMT_LD = ST * SK / 256;  // elements of each operand tile a thread brings in per k step
 
 struct SimtGroupsByValue {  // descriptors travel in the kernel's parameter space: no device-side array, CUDA-graph safe
   SimtGemmGroup g[SIMT_MAX_HOST_GROUPS];
 };
 
+// These launches are latency-bound (M = episodes: a few dozen CTAs, K up to 768 walked in dependent steps), so the operand tiles of
+// step k+1 are requested into registers before the FMAs of step k: one global round trip per step is hidden behind the arithmetic.
+// Every output still accumulates its products in ascending k with fmaf, so the result does not depend on SK or on the prefetch.
 __device__ __forceinline__ void simt_gemm_tile(const SimtGemmGroup& g, int M, int act) {
   const int n0 = blockIdx.x * ST, m0 = blockIdx.y * ST;
   if (n0 >= g.n) return;
@@ -20,14 +24,27 @@ __device__ __forceinline__ void simt_gemm_tile(const SimtGemmGroup& g, int M, in
   __shared__ float ws[SK][ST + 4];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, 4 x 4 outputs each
   float acc[4][4] = {};
-  for (int k0 = 0; k0 < g.k; k0 += SK) {
-    for (int i = threadIdx.x; i < ST * SK; i += 256) {
+  float xr[SIMT_LD], wr[SIMT_LD];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int e = 0; e < SIMT_LD; ++e) {
+      const int i = threadIdx.x + e * 256;
       const int r = i / SK, kk = i % SK;
       const int m = m0 + r, n = n0 + r, k = k0 + kk;
-      xs[kk][r] = (m < M && k < g.k) ? __ldg(g.x + (size_t)m * g.ldx + k) : 0.f;
-      ws[kk][r] = (n < g.n && k < g.k) ? __ldg(g.w + (size_t)n * g.ldw + k) : 0.f;
+      xr[e] = (m < M && k < g.k) ? __ldg(g.x + (size_t)m * g.ldx + k) : 0.f;
+      wr[e] = (n < g.n && k < g.k) ? __ldg(g.w + (size_t)n * g.ldw + k) : 0.f;
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < g.k; k0 += SK) {
+#pragma unroll
+    for (int e = 0; e < SIMT_LD; ++e) {
+      const int i = threadIdx.x + e * 256;
+      xs[i % SK][i / SK] = xr[e];
+      ws[i % SK][i / SK] = wr[e];
     }
     __syncthreads();
+    if (k0 + SK < g.k) fetch(k0 + SK);
 #pragma unroll
     for (int kk = 0; kk < SK; ++kk) {
       float a[4], b[4];
