@@ -1,7 +1,7 @@
 #!/bin/bash
 # round-2 GPU pass L: current tree: kernel tests (SIMT GEMM prefetch), default bench wall time, ragged line, prompt-encode ncu table, step ncu table
 O=gpurun_out/r2l; mkdir -p $O
-timeout 600 python -m pytest tests/test_kernels_gpu.py tests/test_policy_gpu.py -m gpu --timeout 120 -x -q > $O/pytest_kernels_policy.log 2>&1; rc=$?; tail -3 $O/pytest_kernels_policy.log
+timeout 600 python -m pytest tests/test_kernels_gpu.py tests/test_policy_gpu.py tests/test_graph_gpu.py -m gpu --timeout 120 -x -q > $O/pytest_kernels_policy.log 2>&1; rc=$?; tail -3 $O/pytest_kernels_policy.log
 if [ $rc -ne 0 ]; then echo "tests failed (rc=$rc): stopping"; grep -E "timeout|Error|error|assert" $O/pytest_kernels_policy.log | head -20; exit 1; fi
 ( time timeout 900 python bench.py ) > $O/bench_default.json 2> $O/bench_default.err; echo "default rc=$?"; cut -c1-300 $O/bench_default.json; tail -4 $O/bench_default.err
 timeout 300 python bench.py --ragged --steps 6 --warmup 3 --no-cpu-baseline --no-gpu-eager --no-incremental > $O/bench_cfg3_ragged.json 2> $O/bench_cfg3_ragged.err; echo "ragged rc=$?"; cut -c1-300 $O/bench_cfg3_ragged.json
