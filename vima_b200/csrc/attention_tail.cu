@@ -51,11 +51,10 @@ template <int DT>
 __global__ void __launch_bounds__(TAIL_WARPS * 32) attention_tail_kernel(const AttnParams p, int row0, int nt, int lk_pad) {
   extern __shared__ __align__(16) float smt[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long slot = (long long)blockIdx.x * TAIL_WARPS + warp;
-  if (slot >= (long long)p.B * p.H) return;  // whole warps leave; nothing below synchronises across warps
-  // last batch element first: the tcgen05 kernel that ran just before walked the batch upwards, so the K / V rows it touched last
-  // (the ~100 MB that still sit in L2) are the ones read first here
-  const long long unit = (long long)p.B * p.H - 1 - slot;
+  // (batch ascending, like the tcgen05 kernel before it: walking the batch downwards to catch that kernel's last K / V rows in L2
+  //  was measured 45 % SLOWER -- 0.246 vs 0.169 ms per call, profiles/r2l_*)
+  const long long unit = (long long)blockIdx.x * TAIL_WARPS + warp;
+  if (unit >= (long long)p.B * p.H) return;  // whole warps leave; nothing below synchronises across warps
   const int b = (int)(unit / p.H), h = (int)(unit % p.H);
   const int Lk = p.Lk;
   const int kvb = p.kv_batch_rows ? p.kv_batch_rows : Lk;

@@ -74,6 +74,16 @@ __device__ __forceinline__ void fma2(float& x0, float& x1, float s, float n) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(xx));
 }
 
+// (x0, x1) * s + (n0, n1)  as one packed FFMA2
+__device__ __forceinline__ void fma2v(float& x0, float& x1, float s, float n0, float n1) {
+  unsigned long long xx, ss, nn;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(xx) : "f"(x0), "f"(x1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(ss) : "f"(s));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(nn) : "f"(n0), "f"(n1));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(xx) : "l"(xx), "l"(ss), "l"(nn));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(xx));
+}
+
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -316,6 +326,22 @@ __global__ void __launch_bounds__(ATC_THREADS, 3) attention_tc_kernel(const __gr
               }
               mx = fmaxf(m0, m1) * c_l2;
               sc = c_l2;
+            } else if (!needs_causal) {  // padded keys, no causal boundary in this chunk: additive mask terms, packed
+              float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+              for (int c4 = 0; c4 < ATC_KC; c4 += 4) {
+                const float4 m4 = *reinterpret_cast<const float4*>(maskadd + k0 + c4);
+                float x0 = __uint_as_float(sv[c4]), x1 = __uint_as_float(sv[c4 + 1]);
+                float x2 = __uint_as_float(sv[c4 + 2]), x3 = __uint_as_float(sv[c4 + 3]);
+                fma2v(x0, x1, c_l2, m4.x, m4.y);
+                fma2v(x2, x3, c_l2, m4.z, m4.w);
+                sv[c4] = __float_as_uint(x0); sv[c4 + 1] = __float_as_uint(x1);
+                sv[c4 + 2] = __float_as_uint(x2); sv[c4 + 3] = __float_as_uint(x3);
+                m0 = max3(m0, x0, x1);
+                m1 = max3(m1, x2, x3);
+              }
+              mx = fmaxf(m0, m1);
+              sc = 1.f;
             } else {
               mx = -INFINITY;
 #pragma unroll
