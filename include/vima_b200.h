@@ -42,7 +42,8 @@ extern "C" {
 
 enum { VIMA_OK = 0, VIMA_E_INVALID = 1, VIMA_E_CUDA = 2, VIMA_E_UNSUPPORTED = 3 };
 enum { VIMA_DT_F16 = 0, VIMA_DT_BF16 = 1 };
-enum { VIMA_ACT_NONE = 0, VIMA_ACT_RELU = 1, VIMA_ACT_QUICKGELU = 2, VIMA_ACT_GELU = 3 };
+enum { VIMA_ACT_NONE = 0, VIMA_ACT_RELU = 1, VIMA_ACT_QUICKGELU = 2, VIMA_ACT_GELU = 3 /* erf, nn.GELU() */,
+       VIMA_ACT_GELU_TANH = 4 /* HF NewGELUActivation, OpenAIGPTConfig.afn = "gelu" */ };
 
 typedef struct vima_ctx vima_ctx;
 

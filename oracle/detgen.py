@@ -54,7 +54,7 @@ def randint(key: str, shape, low: int, high: int, seed: int = 0, dtype=torch.int
 # weights
 # ------------------------------------------------------------------------------------------------
 _CONV1D = re.compile(r"(^|\.)h\.\d+\.(attn|mlp)\.c_(attn|fc|proj)\.weight$")  # HF Conv1D: weight is [in, out]
-_SKIP = re.compile(r"((^|\.)(position_ids|kv_position_ids|xattn_position_ids)|\.h\.\d+\.attn\.bias)$")  # structural buffers
+_SKIP = re.compile(r"((^|\.)(position_ids|kv_position_ids|xattn_position_ids)|(^|\.)h\.\d+\.attn\.bias)$")  # structural buffers
 
 
 def weight_for(key: str, shape, seed: int = 0) -> torch.Tensor | None:

@@ -72,6 +72,11 @@ def gelu_erf(x):
     return 0.5 * x * (1.0 + torch.erf(x / math.sqrt(2.0)))
 
 
+def gelu_new(x):
+    """HF NewGELUActivation (transformers/activations.py; ACT_FNS["gelu"] of HF:modeling_openai.py, the OpenAIGPTConfig.afn default)."""
+    return 0.5 * x * (1.0 + torch.tanh(math.sqrt(2.0 / math.pi) * (x + 0.044715 * torch.pow(x, 3.0))))
+
+
 def mlp_seq(sd: SD, prefix: str, x: torch.Tensor, idx: Sequence[int]) -> torch.Tensor:
     """build_mlp Sequential (vima/nn/utils.py:84-91): Linear, Identity, ReLU, ..., Linear; Linear sits at idx."""
     for j, i in enumerate(idx):
@@ -104,7 +109,8 @@ def xattention(sd: SD, p: str, q: torch.Tensor, kv: torch.Tensor, kv_mask: torch
     a = linear(ctx, sd[p + "attention_out.weight"]) + q  # :217-218 (residual with UN-normalised q)
     ff = linear(layer_norm(a, sd[p + "ln.weight"], sd[p + "ln.bias"]), sd[p + "linear1.weight"])  # :220-221
     ff = gelu_erf(ff)  # :222 nn.GELU() exact erf
-    ff = ff * linear(a, sd[p + "gated_layer.weight"])  # :223-224 gate reads UN-normalised a
+    if (p + "gated_layer.weight") in sd:  # use_geglu (:139-142)
+        ff = ff * linear(a, sd[p + "gated_layer.weight"])  # :223-224 gate reads UN-normalised a
     ff = linear(ff, sd[p + "linear2.weight"])  # :225
     return ff + a  # :227
 
@@ -133,9 +139,11 @@ def gpt_block(sd: SD, p: str, x: torch.Tensor, add_mask: Optional[torch.Tensor],
     """Block.forward (post-LN), components.py:23-37; MLP.forward GEGLU, components.py:97-102."""
     a = causal_self_attention(sd, p + "attn.", x, add_mask, n_head)
     n = layer_norm(x + a, sd[p + "ln_1.weight"], sd[p + "ln_1.bias"])
-    h = gelu_erf(conv1d_hf(n, sd[p + "mlp.c_fc.weight"], sd[p + "mlp.c_fc.bias"]))
-    if (p + "mlp.gated_layer.weight") in sd:
-        h = h * linear(n, sd[p + "mlp.gated_layer.weight"])  # gate reads the NORMALISED n (:100)
+    h = conv1d_hf(n, sd[p + "mlp.c_fc.weight"], sd[p + "mlp.c_fc.bias"])
+    if (p + "mlp.gated_layer.weight") in sd:  # afn == "geglu": nn.GELU() (:89-91), gate reads the NORMALISED n (:100)
+        h = gelu_erf(h) * linear(n, sd[p + "mlp.gated_layer.weight"])
+    else:  # afn = "gelu" (the OpenAIGPTConfig default) -> ACT_FNS["gelu"] = gelu_new (:92-94)
+        h = gelu_new(h)
     m = conv1d_hf(h, sd[p + "mlp.c_proj.weight"], sd[p + "mlp.c_proj.bias"])
     return layer_norm(n + m, sd[p + "ln_2.weight"], sd[p + "ln_2.bias"])
 

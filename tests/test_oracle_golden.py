@@ -128,3 +128,38 @@ def test_de_discretize_matches_reference_fixture():
     for k in keys:
         assert got[k].dtype == torch.float32
         assert np.array_equal(got[k].numpy(), g[f"out.{k}"]), k
+
+
+def _nongeglu_modules():
+    from tests.golden.make_nongeglu_golden import CFG as c
+    import vima_b200.nn as vnn
+
+    xg = vnn.XAttnGPT(c["E"], n_layer=c["n_layer"], n_head=c["n_head"], dropout=0.1, xattn_n_head=c["xattn_n_head"], xattn_ff_expanding=4,
+                      xattn_n_positions=c["xattn_n_positions"], n_positions=c["n_positions"], use_geglu=False).eval()
+    hf = vnn.HFGPT(n_positions=c["n_positions"], n_embd=c["E"], n_layer=c["n_layer"], n_head=c["n_head"], dropout=0.1, use_geglu=False).eval()
+    detgen.fill_module_(xg)
+    detgen.fill_module_(hf)
+    return c, xg, hf
+
+
+def test_nongeglu_oracle_and_state_dict_match_reference_fixture():
+    """`use_geglu=False` (reference components.py:92-98,139-142,218-225; gpt.py:255-259): act(c_fc(x)) with HF gelu_new in the GPT
+    blocks, gelu(linear1(ln(a))) without a gate in XAttention.  The oracle and our modules' state-dict keys vs the fixture minted
+    from the unmodified reference modules (tests/golden/make_nongeglu_golden.py)."""
+    import os
+
+    from tests.golden.make_nongeglu_golden import inputs
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "nongeglu.npz"))
+    c, xg, hf = _nongeglu_modules()
+    assert sorted(xg.state_dict().keys()) == list(g["xattn_gpt_keys"])
+    assert sorted(k for k in hf.state_dict().keys()) == list(g["hfgpt_keys"])
+    x, pr, pmask, omask, pos, ppos = inputs()
+    sd = {k: v.detach() for k, v in xg.state_dict().items()}
+    y = O.xattn_gpt_forward(sd, "", obs_action_tokens=x, obs_action_position_ids=pos, prompt_tokens=pr, prompt_mask=pmask,
+                            prompt_position_ids=ppos, obs_action_masks=omask, n_layer=c["n_layer"], n_head=c["n_head"],
+                            xattn_n_head=c["xattn_n_head"])
+    assert_close("xattn_gpt(use_geglu=False)", g["xattn_gpt"], y.numpy(), 2e-5)
+    sdh = {k: v.detach() for k, v in hf.state_dict().items()}
+    yh = O.hfgpt_forward(sdh, "", x, omask, pos, c["n_head"])
+    assert_close("hfgpt(use_geglu=False)", g["hfgpt"], yh.numpy(), 2e-5)

@@ -231,3 +231,30 @@ def test_de_discretize_bit_exact_vs_reference_fixture():
     for k in keys:
         assert got[k].dtype == torch.float32
         assert np.array_equal(got[k].cpu().numpy(), g[f"out.{k}"]), k
+
+
+def test_nongeglu_sequence_models_match_reference_fixture():
+    """XAttnGPT / HFGPT with use_geglu=False (GEMM epilogue VIMA_ACT_GELU_TANH = HF gelu_new in the blocks, erf GELU without a gate in
+    XAttention, LayerNorms folded as in the GEGLU path) vs the fixture minted from the unmodified reference modules."""
+    import os
+
+    import vima_b200
+    from tests.golden.make_nongeglu_golden import inputs
+    from tests.test_oracle_golden import _nongeglu_modules
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "nongeglu.npz"))
+    c, xg, hf = _nongeglu_modules()
+    xg, hf = xg.cuda(), hf.cuda()
+    x, pr, pmask, omask, pos, ppos = (t.cuda() for t in inputs())
+    for mode in ("f16x3", "f16f8"):
+        vima_b200.set_precision(mode)
+        try:
+            with torch.no_grad():
+                y = xg(obs_action_tokens=x, obs_action_position_ids=pos, prompt_tokens=pr, prompt_mask=pmask, prompt_position_ids=ppos,
+                       batch_first=False, obs_action_masks=omask)
+                yh = hf(x, custom_mask=omask, position_ids=pos, batch_first=False)
+        finally:
+            vima_b200.set_precision("f16x3")
+        ex, eh = rel_l2(g["xattn_gpt"], y.cpu().numpy()), rel_l2(g["hfgpt"], yh.cpu().numpy())
+        print(mode, f"xattn_gpt {ex:.1e} hfgpt {eh:.1e}")
+        assert ex <= TOL and eh <= TOL, (mode, ex, eh)

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libvima_b200.so")
 
 DT_F16, DT_BF16 = 0, 1
-ACT_NONE, ACT_RELU, ACT_QUICKGELU, ACT_GELU = 0, 1, 2, 3
+ACT_NONE, ACT_RELU, ACT_QUICKGELU, ACT_GELU, ACT_GELU_TANH = 0, 1, 2, 3, 4
 
 c_void_p, c_int, c_float, c_i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
 

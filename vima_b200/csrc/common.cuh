@@ -14,7 +14,7 @@
 namespace vima {
 
 enum : int { DT_F16 = 0, DT_BF16 = 1 };
-enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_QUICKGELU = 2, ACT_GELU = 3 };
+enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_QUICKGELU = 2, ACT_GELU = 3, ACT_GELU_TANH = 4 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -117,11 +117,20 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
 __device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
+// HF NewGELUActivation ("gelu_new", OpenAIGPTConfig.afn = "gelu"): 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))), with
+// tanh(u) = 1 - 2 / (1 + e^{2u}) on ex2.approx / rcp.approx (absolute error ~2e-7; saturates correctly at both ends)
+__device__ __forceinline__ float gelu_tanh(float x) {
+  const float u = 0.7978845608028654f * fmaf(0.044715f * x * x, x, x);
+  const float e = ex2_approx(u * 2.8853900817779268f);  // e^{2u}
+  const float th = 1.0f - __fdividef(2.0f, 1.0f + e);
+  return 0.5f * x * (1.0f + th);
+}
 __device__ __forceinline__ float apply_act(int act, float x) {
   switch (act) {
     case ACT_RELU: return fmaxf(x, 0.f);
     case ACT_QUICKGELU: return quick_gelu(x);
     case ACT_GELU: return gelu_erf(x);
+    case ACT_GELU_TANH: return gelu_tanh(x);
     default: return x;
   }
 }

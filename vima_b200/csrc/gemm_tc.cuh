@@ -98,6 +98,7 @@ __device__ __forceinline__ float act_ct(float x) {
   if constexpr (ACT == ACT_RELU) return fmaxf(x, 0.f);
   else if constexpr (ACT == ACT_QUICKGELU) return quick_gelu(x);
   else if constexpr (ACT == ACT_GELU) return gelu_erf(x);
+  else if constexpr (ACT == ACT_GELU_TANH) return gelu_tanh(x);
   else return x;
 }
 

@@ -56,15 +56,20 @@ class Block(nn.Module):
 
 
 def pack_block(ctx, blk: "Block", p) -> dict:
-    """Packed weights of one GPT block.  ln_1 is folded into c_fc || gated_layer (both read ln_1(s), components.py:31-36)."""
+    """Packed weights of one GPT block.  ln_1 is folded into c_fc || gated_layer (both read ln_1(s), components.py:31-36); without
+    GEGLU (`afn != "geglu"`, components.py:92-94) into c_fc alone."""
     ln1 = (blk.ln_1.weight.detach(), blk.ln_1.bias.detach())
-    return {
+    d = {
         "c_attn": eng.pack_linear(ctx, blk.attn.c_attn.weight, blk.attn.c_attn.bias, transposed=True, p=p, f8=True),
         "c_proj": eng.pack_linear(ctx, blk.attn.c_proj.weight, blk.attn.c_proj.bias, transposed=True, p=p, f8=True),
-        "fc_glu": eng.pack_glu(ctx, blk.mlp.c_fc.weight, blk.mlp.c_fc.bias, blk.mlp.gated_layer.weight, val_transposed=True,
-                               gate_transposed=False, p=p, f8=True, ln=ln1, ln_gate=True),
         "mlp_proj": eng.pack_linear(ctx, blk.mlp.c_proj.weight, blk.mlp.c_proj.bias, transposed=True, p=p, f8=True),
     }
+    if blk.mlp.gated_layer is not None:
+        d["fc_glu"] = eng.pack_glu(ctx, blk.mlp.c_fc.weight, blk.mlp.c_fc.bias, blk.mlp.gated_layer.weight, val_transposed=True,
+                                   gate_transposed=False, p=p, f8=True, ln=ln1, ln_gate=True)
+    else:
+        d["fc"] = eng.pack_linear(ctx, blk.mlp.c_fc.weight, blk.mlp.c_fc.bias, transposed=True, p=p, f8=True, ln=ln1)
+    return d
 
 
 class DecodeCache:
@@ -132,7 +137,10 @@ def run_block(ctx, p, W, blk: "Block", x32, x16, c16, *, B, L, E, H, omask, chai
     part = eng.stats_buffer(ctx, M, W["c_proj"], dev)
     s32, s16 = eng.gemm(ctx, c16, W["c_proj"], p, residual=x32, want_f32=True, want16=True, out_f8=True, stats_out=part)
     st = eng.row_stats_of(ctx, part, M, E, blk.ln_1.eps)
-    _, h16 = eng.gemm(ctx, s16, W["fc_glu"], p, act=_C.ACT_GELU, want16=True, out_f8=True, row_stats=st)
+    if "fc_glu" in W:
+        _, h16 = eng.gemm(ctx, s16, W["fc_glu"], p, act=_C.ACT_GELU, want16=True, out_f8=True, row_stats=st)
+    else:  # afn = "gelu" (HF NewGELUActivation, the OpenAIGPTConfig default): act(c_fc(ln_1(s))), components.py:92-98
+        _, h16 = eng.gemm(ctx, s16, W["fc"], p, act=_C.ACT_GELU_TANH, want16=True, out_f8=True, row_stats=st)
     t32, _ = eng.gemm(ctx, h16, W["mlp_proj"], p, residual=s32, res_ln=(st, blk.ln_1.weight.detach(), blk.ln_1.bias.detach()), want_f32=True)
     del h16, s32, s16
     w, b = blk.ln_2.weight.detach(), blk.ln_2.bias.detach()
@@ -232,8 +240,6 @@ class XAttnGPT(nn.Module):
         use_geglu: bool = False,
     ):
         super().__init__()
-        if not use_geglu:
-            raise NotImplementedError("vima_b200.XAttnGPT implements the GEGLU configuration every VIMA checkpoint uses")
         self.embd_dim, self.n_layer, self.n_head, self.xattn_n_head = embd_dim, n_layer, n_head, xattn_n_head
         self.n_positions, self.xattn_n_positions = n_positions, xattn_n_positions
         self.positions_embed = nn.Embedding(n_positions, embd_dim)
@@ -267,8 +273,12 @@ class XAttnGPT(nn.Module):
                 d["wo"] = eng.pack_linear(ctx, xa.attention_out.weight, None, transposed=False, p=p, f8=True)
                 # linear1 reads ln(a), the gate reads a itself (components.py:218-221): one GEGLU GEMM over the un-normalised a with
                 # `ln` folded into the value half only
-                d["w1g"] = eng.pack_glu(ctx, xa.linear1.weight, None, xa.gated_layer.weight, val_transposed=False, gate_transposed=False,
-                                        p=p, f8=True, ln=(xa.ln.weight.detach(), xa.ln.bias.detach()), ln_gate=False)
+                xln = (xa.ln.weight.detach(), xa.ln.bias.detach())
+                if xa.gated_layer is not None:
+                    d["w1g"] = eng.pack_glu(ctx, xa.linear1.weight, None, xa.gated_layer.weight, val_transposed=False, gate_transposed=False,
+                                            p=p, f8=True, ln=xln, ln_gate=False)
+                else:  # use_geglu=False (components.py:139-142,218-223): gelu(linear1(ln(a))), no gate
+                    d["w1"] = eng.pack_linear(ctx, xa.linear1.weight, None, transposed=False, p=p, f8=True, ln=xln)
                 d["w2"] = eng.pack_linear(ctx, xa.linear2.weight, None, transposed=False, p=p, f8=True)
                 d.update(pack_block(ctx, blk, p))
                 L.append(d)
@@ -391,7 +401,7 @@ class XAttnGPT(nn.Module):
             part = eng.stats_buffer(ctx, M, W["wo"], dev)
             a32, a16 = eng.gemm(ctx, c16, W["wo"], p, residual=x32, want_f32=True, want16=True, out_f8=True, stats_out=part)
             st = eng.row_stats_of(ctx, part, M, E, xa.ln.eps)
-            _, h16 = eng.gemm(ctx, a16, W["w1g"], p, act=_C.ACT_GELU, want16=True, out_f8=True, row_stats=st)
+            _, h16 = eng.gemm(ctx, a16, W["w1g"] if "w1g" in W else W["w1"], p, act=_C.ACT_GELU, want16=True, out_f8=True, row_stats=st)
             xb32, xb16 = eng.gemm(ctx, h16, W["w2"], p, residual=a32, want_f32=True, want16=True, out_f8=True)
             del h16, a32, a16
             # ---------------- causal Block ----------------
@@ -419,13 +429,11 @@ class _OpenAIGPTModel(nn.Module):
 
 
 class HFGPT(nn.Module):
-    """Decoder-only GPT-1 stack with GEGLU (reference: vima/nn/seq_modeling/gpt/gpt.py:15-301) -- the VIMA-Gato baseline's
+    """Decoder-only GPT-1 stack, GEGLU or plain gelu_new MLPs (reference: vima/nn/seq_modeling/gpt/gpt.py:15-301) -- the VIMA-Gato baseline's
     sequence model.  Same Block kernels as XAttnGPT (causal-only path, BASELINE.json configs[4])."""
 
     def __init__(self, *, vocab_size=40478, n_positions=512, n_embd=768, n_layer=12, n_head=12, dropout: float = 0.1, use_geglu: bool = False):
         super().__init__()
-        if not use_geglu:
-            raise NotImplementedError("vima_b200.HFGPT implements the GEGLU configuration VIMA-Gato uses")
         self.n_embd, self.n_layer, self.n_head, self.n_positions = n_embd, n_layer, n_head, n_positions
         self.lm = _OpenAIGPTModel(vocab_size, n_positions, n_embd, n_layer, n_head, use_geglu)
         for m in self.modules():
